@@ -1,0 +1,430 @@
+// gort_abi.cu -- the extern "C" boundary of libgort_b200 (include/gort_b200.h): context, device
+// scratch management, host-pointer wrappers (H2D -> kernels -> D2H) and the LUT text layout.
+// No model arithmetic lives here; there is no CPU fallback.
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include "gort_internal.h"
+#include "../data/gort_tables.h"
+
+static char g_create_error[512] = "";
+
+namespace gort {
+
+int set_error(gort_ctx *ctx, int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(ctx ? ctx->err : g_create_error, 512, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int check_cuda(gort_ctx *ctx, cudaError_t e, const char *what)
+{
+    if (e == cudaSuccess) return GORT_OK;
+    return set_error(ctx, GORT_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+static void *grow(gort_ctx *ctx, void **p, size_t *cap, size_t bytes)
+{
+    if (bytes == 0) bytes = 8;
+    if (*cap >= bytes) return *p;
+    // the buffer may still be in use by work enqueued earlier (on the context's stream or on a
+    // caller-supplied one); regrowth is rare, so wait for the whole device
+    cudaDeviceSynchronize();
+    if (*p) cudaFree(*p);
+    *p = NULL; *cap = 0;
+    size_t want = bytes + bytes / 8;
+    cudaError_t e = cudaMalloc(p, want);
+    if (e != cudaSuccess) { e = cudaMalloc(p, bytes); want = bytes; }
+    if (e != cudaSuccess) { *p = NULL; set_error(ctx, GORT_ERR_NOMEM, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e)); return NULL; }
+    *cap = want;
+    return *p;
+}
+
+void *scratch(gort_ctx *ctx, int slot, size_t bytes) { return grow(ctx, &ctx->scratch[slot], &ctx->scratch_cap[slot], bytes); }
+void *workspace(gort_ctx *ctx, size_t bytes) { return grow(ctx, &ctx->work, &ctx->work_cap, bytes); }
+
+}  // namespace gort
+
+using namespace gort;
+
+#define TRY(x) do { int _r = (x); if (_r != GORT_OK) return _r; } while (0)
+#define TRYCUDA(ctx, x, what) do { int _r = check_cuda(ctx, (x), what); if (_r != GORT_OK) return _r; } while (0)
+
+extern "C" {
+
+int gort_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+int gort_create(int device, gort_ctx **out)
+{
+    if (!out) return set_error(NULL, GORT_ERR_INVALID, "gort_create: out is NULL");
+    *out = NULL;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return set_error(NULL, GORT_ERR_CUDA, "gort_create: no CUDA device (%s); this library has no CPU path",
+                         e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= n) return set_error(NULL, GORT_ERR_INVALID, "gort_create: device %d out of range (0..%d)", device, n - 1);
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) return set_error(NULL, GORT_ERR_CUDA, "cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
+    gort_ctx *ctx = (gort_ctx *) calloc(1, sizeof(gort_ctx));
+    if (!ctx) return set_error(NULL, GORT_ERR_NOMEM, "out of host memory");
+    ctx->device = device;
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) { set_error(NULL, GORT_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e)); free(ctx); return GORT_ERR_CUDA; }
+    ctx->sm_count = prop.multiProcessorCount;
+    e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { set_error(NULL, GORT_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); free(ctx); return GORT_ERR_CUDA; }
+    int rc = GORT_OK;
+    if (cudaMalloc((void **) &ctx->d_gauleg, sizeof(double) * 2 * GORT_NQUAD) != cudaSuccess ||
+        cudaMalloc((void **) &ctx->d_prospect, sizeof(double) * 9 * GORT_PROSPECT_NW) != cudaSuccess ||
+        cudaMalloc((void **) &ctx->d_soil, sizeof(double) * 4 * GORT_SOIL_NW) != cudaSuccess)
+        rc = set_error(ctx, GORT_ERR_NOMEM, "cudaMalloc of constant tables failed");
+    if (rc == GORT_OK) rc = launch_gauleg(ctx, ctx->stream, ctx->d_gauleg);
+    if (rc == GORT_OK) rc = launch_tav_tables(ctx, ctx->stream, ctx->d_prospect);
+    if (rc == GORT_OK) rc = upload_soil_tables(ctx, ctx->stream, ctx->d_soil);
+    if (rc == GORT_OK) rc = check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "context initialisation");
+    if (rc != GORT_OK) {
+        strncpy(g_create_error, ctx->err, sizeof g_create_error - 1);
+        gort_destroy(ctx);
+        return rc;
+    }
+    *out = ctx;
+    return GORT_OK;
+}
+
+void gort_destroy(gort_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (int i = 0; i < GORT_NSCRATCH; i++) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
+    if (ctx->work) cudaFree(ctx->work);
+    if (ctx->d_gauleg) cudaFree(ctx->d_gauleg);
+    if (ctx->d_prospect) cudaFree(ctx->d_prospect);
+    if (ctx->d_soil) cudaFree(ctx->d_soil);
+    if (ctx->prof_ev) { for (int i = 0; i < 3 * ctx->prof_cap; i++) cudaEventDestroy(ctx->prof_ev[i]); free(ctx->prof_ev); }
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    free(ctx);
+}
+
+const char *gort_last_error(const gort_ctx *ctx) { return ctx ? ctx->err : g_create_error; }
+void *gort_stream(gort_ctx *ctx) { return ctx ? (void *) ctx->stream : NULL; }
+long gort_launch_count(const gort_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int gort_synchronize(gort_ctx *ctx)
+{
+    if (!ctx) return GORT_ERR_INVALID;
+    return check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "synchronize");
+}
+
+void *gort_host_alloc(size_t bytes)
+{
+    void *p = NULL;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) return NULL;
+    return p;
+}
+
+void gort_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+static cudaStream_t pick(gort_ctx *ctx, void *stream) { return stream ? (cudaStream_t) stream : ctx->stream; }
+
+static int h2d(gort_ctx *ctx, int slot, const double *h, size_t n, double **d)
+{
+    *d = NULL;
+    if (!h || n == 0) return GORT_OK;
+    double *p = (double *) scratch(ctx, slot, n * sizeof(double));
+    if (!p) return GORT_ERR_NOMEM;
+    TRYCUDA(ctx, cudaMemcpyAsync(p, h, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream), "host to device copy");
+    *d = p;
+    return GORT_OK;
+}
+
+static int dout(gort_ctx *ctx, int slot, const double *h, size_t n, double **d)
+{
+    *d = NULL;
+    if (!h || n == 0) return GORT_OK;
+    double *p = (double *) scratch(ctx, slot, n * sizeof(double));
+    if (!p) return GORT_ERR_NOMEM;
+    *d = p;
+    return GORT_OK;
+}
+
+static int d2h(gort_ctx *ctx, double *h, const double *d, size_t n)
+{
+    if (!h || !d || n == 0) return GORT_OK;
+    TRYCUDA(ctx, cudaMemcpyAsync(h, d, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream), "device to host copy");
+    return GORT_OK;
+}
+
+// ---- gap probabilities --------------------------------------------------------------------------
+int gort_lut_batch_dev(gort_ctx *ctx, void *stream, int n_sets, const double *structure, int method, double *lut)
+{
+    if (!ctx) return GORT_ERR_INVALID;
+    if (!structure || !lut || n_sets <= 0) return set_error(ctx, GORT_ERR_INVALID, "gort_lut_batch: bad arguments");
+    if (method != GORT_LUT_FULL && method != GORT_LUT_Q08) return set_error(ctx, GORT_ERR_INVALID, "gort_lut_batch: unknown method %d", method);
+    TRYCUDA(ctx, cudaSetDevice(ctx->device), "cudaSetDevice");
+    return launch_lut(ctx, pick(ctx, stream), n_sets, structure, method, lut);
+}
+
+int gort_lut_batch(gort_ctx *ctx, int n_sets, const double *structure, int method, double *lut)
+{
+    if (!ctx) return GORT_ERR_INVALID;
+    if (!structure || !lut || n_sets <= 0) return set_error(ctx, GORT_ERR_INVALID, "gort_lut_batch: bad arguments");
+    TRYCUDA(ctx, cudaSetDevice(ctx->device), "cudaSetDevice");
+    double *d_st, *d_lut;
+    TRY(h2d(ctx, 0, structure, (size_t) 6 * n_sets, &d_st));
+    TRY(dout(ctx, 1, lut, (size_t) n_sets * GORT_LUT_STRIDE, &d_lut));
+    TRY(gort_lut_batch_dev(ctx, NULL, n_sets, d_st, method, d_lut));
+    TRY(d2h(ctx, lut, d_lut, (size_t) n_sets * GORT_LUT_STRIDE));
+    return check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "gort_lut_batch");
+}
+
+// ---- spectra ------------------------------------------------------------------------------------
+int gort_spectra_batch_dev(gort_ctx *ctx, void *stream, int n_sets, const double *leaf, const double *soil,
+                           double user_leaf, double user_soil, int n_wl, const double *wavelength,
+                           double *rleaf, double *tleaf, double *rsoil)
+{
+    if (!ctx) return GORT_ERR_INVALID;
+    if (!wavelength || !rleaf || !tleaf || !rsoil) return set_error(ctx, GORT_ERR_INVALID, "gort_spectra_batch: NULL argument");
+    TRYCUDA(ctx, cudaSetDevice(ctx->device), "cudaSetDevice");
+    return launch_spectra(ctx, pick(ctx, stream), n_sets, leaf, soil, user_leaf, user_soil, n_wl, wavelength, rleaf, tleaf, rsoil);
+}
+
+int gort_spectra_batch(gort_ctx *ctx, int n_sets, const double *leaf, const double *soil,
+                       double user_leaf, double user_soil, int n_wl, const double *wavelength,
+                       double *rleaf, double *tleaf, double *rsoil)
+{
+    if (!ctx) return GORT_ERR_INVALID;
+    if (!wavelength || !rleaf || !tleaf || !rsoil || n_sets <= 0 || n_wl <= 0)
+        return set_error(ctx, GORT_ERR_INVALID, "gort_spectra_batch: bad arguments");
+    for (int i = 0; i < n_wl; i++)
+        if (wavelength[i] < GORT_WL_MIN || wavelength[i] > GORT_WL_MAX)
+            return set_error(ctx, GORT_ERR_RANGE, "wavlength out of range (400-2500)");   /* sic, gortt.c:1300 */
+    TRYCUDA(ctx, cudaSetDevice(ctx->device), "cudaSetDevice");
+    double *d_leaf, *d_soil, *d_wl, *d_rl, *d_tl, *d_rs;
+    size_t n = (size_t) n_sets * n_wl;
+    TRY(h2d(ctx, 0, user_leaf < 0.0 ? leaf : NULL, (size_t) 7 * n_sets, &d_leaf));
+    TRY(h2d(ctx, 1, user_soil < 0.0 ? soil : NULL, (size_t) 4 * n_sets, &d_soil));
+    TRY(h2d(ctx, 2, wavelength, n_wl, &d_wl));
+    TRY(dout(ctx, 3, rleaf, n, &d_rl));
+    TRY(dout(ctx, 4, tleaf, n, &d_tl));
+    TRY(dout(ctx, 5, rsoil, n, &d_rs));
+    TRY(gort_spectra_batch_dev(ctx, NULL, n_sets, d_leaf, d_soil, user_leaf, user_soil, n_wl, d_wl, d_rl, d_tl, d_rs));
+    TRY(d2h(ctx, rleaf, d_rl, n));
+    TRY(d2h(ctx, tleaf, d_tl, n));
+    TRY(d2h(ctx, rsoil, d_rs, n));
+    return check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "gort_spectra_batch");
+}
+
+int gort_prospect_batch(gort_ctx *ctx, int n_sets, const double *leaf, double *refl, double *tran)
+{
+    if (!ctx) return GORT_ERR_INVALID;
+    if (!leaf || !refl || !tran || n_sets <= 0) return set_error(ctx, GORT_ERR_INVALID, "gort_prospect_batch: bad arguments");
+    TRYCUDA(ctx, cudaSetDevice(ctx->device), "cudaSetDevice");
+    double *d_leaf, *d_r, *d_t;
+    size_t n = (size_t) n_sets * GORT_PROSPECT_NW;
+    TRY(h2d(ctx, 0, leaf, (size_t) 7 * n_sets, &d_leaf));
+    TRY(dout(ctx, 1, refl, n, &d_r));
+    TRY(dout(ctx, 2, tran, n, &d_t));
+    TRY(launch_prospect_full(ctx, ctx->stream, n_sets, d_leaf, d_r, d_t));
+    TRY(d2h(ctx, refl, d_r, n));
+    TRY(d2h(ctx, tran, d_t, n));
+    return check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "gort_prospect_batch");
+}
+
+// ---- BRDF / energy --------------------------------------------------------------------------------
+static int check_shape(gort_ctx *ctx, const gort_shape *sh, const char *who)
+{
+    if (!sh) return set_error(ctx, GORT_ERR_INVALID, "%s: shape is NULL", who);
+    if (sh->n_sets <= 0 || sh->n_geom <= 0 || sh->n_wl <= 0)
+        return set_error(ctx, GORT_ERR_INVALID, "%s: n_sets, n_geom and n_wl must be positive", who);
+    if ((long) sh->n_sets * sh->n_geom > 2000000000L)
+        return set_error(ctx, GORT_ERR_INVALID, "%s: n_sets*n_geom too large", who);
+    return GORT_OK;
+}
+
+int gort_brdf_batch_dev(gort_ctx *ctx, void *stream, const gort_shape *shape, const double *structure,
+                        const double *lut, const double *angles, const double *rleaf, const double *tleaf,
+                        const double *rsoil, double *rsurf, double *scomp, double *kprop)
+{
+    if (!ctx) return GORT_ERR_INVALID;
+    TRY(check_shape(ctx, shape, "gort_brdf_batch"));
+    if (!structure || !lut || !angles || !rleaf || !tleaf || !rsoil || !rsurf)
+        return set_error(ctx, GORT_ERR_INVALID, "gort_brdf_batch: NULL argument");
+    TRYCUDA(ctx, cudaSetDevice(ctx->device), "cudaSetDevice");
+    return launch_brdf(ctx, pick(ctx, stream), *shape, structure, lut, angles, rleaf, tleaf, rsoil, rsurf, scomp, kprop);
+}
+
+struct Staged { double *st, *lut, *ang, *rl, *tl, *rs; };
+
+static int stage_inputs(gort_ctx *ctx, const gort_shape *sh, const double *structure, const double *lut,
+                        const double *angles, const double *rleaf, const double *tleaf, const double *rsoil, Staged *d)
+{
+    size_t M = sh->n_sets, G = sh->n_geom, W = sh->n_wl;
+    size_t na = sh->geom_per_set ? M * G : G;
+    size_t ns = sh->spectra_per_set ? M * W : W;
+    TRY(h2d(ctx, 0, structure, 6 * M, &d->st));
+    TRY(h2d(ctx, 1, lut, M * GORT_LUT_STRIDE, &d->lut));
+    TRY(h2d(ctx, 2, angles, 4 * na, &d->ang));
+    TRY(h2d(ctx, 3, rleaf, ns, &d->rl));
+    TRY(h2d(ctx, 4, tleaf, ns, &d->tl));
+    TRY(h2d(ctx, 5, rsoil, ns, &d->rs));
+    return GORT_OK;
+}
+
+int gort_brdf_batch(gort_ctx *ctx, const gort_shape *shape, const double *structure, const double *lut,
+                    const double *angles, const double *rleaf, const double *tleaf, const double *rsoil,
+                    double *rsurf, double *scomp, double *kprop)
+{
+    if (!ctx) return GORT_ERR_INVALID;
+    TRY(check_shape(ctx, shape, "gort_brdf_batch"));
+    if (!structure || !lut || !angles || !rleaf || !tleaf || !rsoil || !rsurf)
+        return set_error(ctx, GORT_ERR_INVALID, "gort_brdf_batch: NULL argument");
+    TRYCUDA(ctx, cudaSetDevice(ctx->device), "cudaSetDevice");
+    Staged d;
+    TRY(stage_inputs(ctx, shape, structure, lut, angles, rleaf, tleaf, rsoil, &d));
+    size_t n = (size_t) shape->n_sets * shape->n_geom * shape->n_wl;
+    size_t nl = (size_t) shape->n_sets * shape->n_geom;
+    double *d_rsurf, *d_scomp, *d_kprop;
+    TRY(dout(ctx, 6, rsurf, n, &d_rsurf));
+    TRY(dout(ctx, 7, scomp, 4 * n, &d_scomp));
+    TRY(dout(ctx, 8, kprop, 4 * nl, &d_kprop));
+    TRY(launch_brdf(ctx, ctx->stream, *shape, d.st, d.lut, d.ang, d.rl, d.tl, d.rs, d_rsurf, d_scomp, d_kprop));
+    TRY(d2h(ctx, rsurf, d_rsurf, n));
+    TRY(d2h(ctx, scomp, d_scomp, 4 * n));
+    TRY(d2h(ctx, kprop, d_kprop, 4 * nl));
+    return check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "gort_brdf_batch");
+}
+
+int gort_energy_batch_dev(gort_ctx *ctx, void *stream, const gort_shape *shape, const double *structure,
+                          const double *lut, const double *angles, const double *rleaf, const double *tleaf,
+                          const double *rsoil, double *albedo, double *favegt, double *fasoil)
+{
+    if (!ctx) return GORT_ERR_INVALID;
+    TRY(check_shape(ctx, shape, "gort_energy_batch"));
+    if (!structure || !lut || !angles || !rleaf || !tleaf || !rsoil || !albedo || !favegt || !fasoil)
+        return set_error(ctx, GORT_ERR_INVALID, "gort_energy_batch: NULL argument");
+    TRYCUDA(ctx, cudaSetDevice(ctx->device), "cudaSetDevice");
+    return launch_energy(ctx, pick(ctx, stream), *shape, structure, lut, angles, rleaf, tleaf, rsoil, albedo, favegt, fasoil);
+}
+
+int gort_energy_batch(gort_ctx *ctx, const gort_shape *shape, const double *structure, const double *lut,
+                      const double *angles, const double *rleaf, const double *tleaf, const double *rsoil,
+                      double *albedo, double *favegt, double *fasoil)
+{
+    if (!ctx) return GORT_ERR_INVALID;
+    TRY(check_shape(ctx, shape, "gort_energy_batch"));
+    if (!structure || !lut || !angles || !rleaf || !tleaf || !rsoil || !albedo || !favegt || !fasoil)
+        return set_error(ctx, GORT_ERR_INVALID, "gort_energy_batch: NULL argument");
+    TRYCUDA(ctx, cudaSetDevice(ctx->device), "cudaSetDevice");
+    Staged d;
+    TRY(stage_inputs(ctx, shape, structure, lut, angles, rleaf, tleaf, rsoil, &d));
+    size_t n = (size_t) shape->n_sets * shape->n_geom * shape->n_wl;
+    double *d_a, *d_v, *d_s;
+    TRY(dout(ctx, 6, albedo, n, &d_a));
+    TRY(dout(ctx, 7, favegt, n, &d_v));
+    TRY(dout(ctx, 8, fasoil, n, &d_s));
+    TRY(launch_energy(ctx, ctx->stream, *shape, d.st, d.lut, d.ang, d.rl, d.tl, d.rs, d_a, d_v, d_s));
+    TRY(d2h(ctx, albedo, d_a, n));
+    TRY(d2h(ctx, favegt, d_v, n));
+    TRY(d2h(ctx, fasoil, d_s, n));
+    return check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "gort_energy_batch");
+}
+
+int gort_gauleg(gort_ctx *ctx, double *abscissa, double *weights)
+{
+    if (!ctx || !abscissa || !weights) return GORT_ERR_INVALID;
+    TRYCUDA(ctx, cudaSetDevice(ctx->device), "cudaSetDevice");
+    TRYCUDA(ctx, cudaMemcpyAsync(abscissa, ctx->d_gauleg, sizeof(double) * GORT_NQUAD, cudaMemcpyDeviceToHost, ctx->stream), "gauleg copy");
+    TRYCUDA(ctx, cudaMemcpyAsync(weights, ctx->d_gauleg + GORT_NQUAD, sizeof(double) * GORT_NQUAD, cudaMemcpyDeviceToHost, ctx->stream), "gauleg copy");
+    return check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "gort_gauleg");
+}
+
+int gort_dfma_peak(gort_ctx *ctx, double *tflops)
+{
+    if (!ctx || !tflops) return GORT_ERR_INVALID;
+    TRYCUDA(ctx, cudaSetDevice(ctx->device), "cudaSetDevice");
+    return launch_dfma_peak(ctx, ctx->stream, tflops);
+}
+
+int gort_profile_begin(gort_ctx *ctx, int max_steps)
+{
+    if (!ctx || max_steps <= 0) return GORT_ERR_INVALID;
+    TRYCUDA(ctx, cudaSetDevice(ctx->device), "cudaSetDevice");
+    if (ctx->prof_ev) { for (int i = 0; i < 3 * ctx->prof_cap; i++) cudaEventDestroy(ctx->prof_ev[i]); free(ctx->prof_ev); ctx->prof_ev = NULL; }
+    ctx->prof_ev = (cudaEvent_t *) calloc((size_t) 3 * max_steps, sizeof(cudaEvent_t));
+    if (!ctx->prof_ev) return set_error(ctx, GORT_ERR_NOMEM, "out of host memory");
+    for (int i = 0; i < 3 * max_steps; i++) TRYCUDA(ctx, cudaEventCreate(&ctx->prof_ev[i]), "cudaEventCreate");
+    ctx->prof_cap = max_steps;
+    ctx->prof_n = 0;
+    return GORT_OK;
+}
+
+int gort_profile_end(gort_ctx *ctx, double *geom_ms, double *rsurf_ms, int *n_steps)
+{
+    if (!ctx || !ctx->prof_ev) return GORT_ERR_INVALID;
+    TRYCUDA(ctx, cudaSetDevice(ctx->device), "cudaSetDevice");
+    double g = 0, r = 0;
+    int n = ctx->prof_n;
+    for (int i = 0; i < n; i++) {
+        float a = 0, b = 0;
+        TRYCUDA(ctx, cudaEventSynchronize(ctx->prof_ev[3 * i + 2]), "cudaEventSynchronize");
+        TRYCUDA(ctx, cudaEventElapsedTime(&a, ctx->prof_ev[3 * i], ctx->prof_ev[3 * i + 1]), "cudaEventElapsedTime");
+        TRYCUDA(ctx, cudaEventElapsedTime(&b, ctx->prof_ev[3 * i + 1], ctx->prof_ev[3 * i + 2]), "cudaEventElapsedTime");
+        g += a; r += b;
+    }
+    for (int i = 0; i < 3 * ctx->prof_cap; i++) cudaEventDestroy(ctx->prof_ev[i]);
+    free(ctx->prof_ev);
+    ctx->prof_ev = NULL; ctx->prof_cap = 0; ctx->prof_n = 0;
+    if (geom_ms) *geom_ms = n ? g / n : 0.0;
+    if (rsurf_ms) *rsurf_ms = n ? r / n : 0.0;
+    if (n_steps) *n_steps = n;
+    return GORT_OK;
+}
+
+// ---- LUT text layout, gortt.c:123-146 -------------------------------------------------------------
+long gort_lut_write_text(const double *lut, void *fp)
+{
+    if (!lut || !fp) return -GORT_ERR_INVALID;
+    FILE *f = (FILE *) fp;
+    long n = 0;
+    for (int j = 0; j < GORT_LUT_FILE_ROWS; j++) {
+        int k = fprintf(f, "%d %0.40f %0.40f\n", j, lut[j], lut[GORT_NTH + j]);
+        if (k < 0) return -GORT_ERR_IO;
+        n += k;
+    }
+    int k = fprintf(f, "-1 %0.40f %0.40f\n", lut[2 * GORT_NTH], lut[2 * GORT_NTH + 1]);
+    if (k < 0) return -GORT_ERR_IO;
+    return n + k;
+}
+
+int gort_lut_read_text(const char *path, double *lut)
+{
+    if (!path || !lut) return GORT_ERR_INVALID;
+    FILE *f = fopen(path, "r");
+    if (!f) return GORT_ERR_IO;
+    int j;
+    double x1, x2;
+    while (fscanf(f, "%d %lf %lf", &j, &x1, &x2) == 3) {
+        if (j >= 0) {
+            if (j < GORT_NTH) { lut[j] = x1; lut[GORT_NTH + j] = x2; }   /* the reference has no bound */
+        } else {
+            lut[2 * GORT_NTH] = x1;
+            lut[2 * GORT_NTH + 1] = x2;
+        }
+    }
+    fclose(f);
+    return GORT_OK;
+}
+
+}  // extern "C"

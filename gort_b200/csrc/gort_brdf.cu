@@ -1,0 +1,373 @@
+// gort_brdf.cu -- BRDF and energy-balance kernels (sm_100a, FP64, no tensor cores: nothing here
+// is a dense contraction).
+//
+//   geom_kernel        one thread per (parameter set, input line): everything gortt_rsurf does
+//                      before its wavelength loop (gortt.c:240-291, :424-449, gortt_brdf.c:7-238,
+//                      :638-702) -> 13-double geometry record, SoA in HBM.
+//   rsurf_wide_kernel  W >= 64: one CTA per (line tile, wavelength chunk); the tile's records are
+//                      staged in shared memory, each thread owns wavelengths and walks the lines,
+//                      re-deriving (set, lambda) terms only when the set changes and
+//                      (sun, lambda) terms only when the sun changes.  Coalesced FP64 stores.
+//   rsurf_flat_kernel  W < 64 (band sets): one thread per (line, band).
+//   energy_kernel      one CTA per (set, sun line): 512 quadrature nodes' records in shared
+//                      memory, lanes = azimuth nodes, warp-shuffle reduction (gortt_albedo.c).
+#include "gort_device.cuh"
+#include "gort_internal.h"
+
+namespace gort {
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+geom_kernel(int n_sets, int n_geom, int geom_per_set, gort_options opt,
+            const double* __restrict__ structure, const double* __restrict__ lut,
+            const double* __restrict__ angles, double* __restrict__ rec, double* __restrict__ kprop)
+{
+    const long L = (long) n_sets * n_geom;
+    long line = (long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (line >= L) return;
+    int m = (int) (line / n_geom);
+    long a = geom_per_set ? line : (line - (long) m * n_geom);
+    long na = geom_per_set ? L : n_geom;
+    Canopy c = canopy_load(structure, n_sets, m, lut);
+    Line g = line_from_degrees(angles[0 * na + a], angles[1 * na + a], angles[2 * na + a], angles[3 * na + a]);
+    double fd = opt.use_fd ? opt.fd : cos(g.sza) / (cos(g.sza) + 0.09);       // gortt.c:290-291
+    GeomRec r = geom_record(c, lut + (size_t) m * GORT_LUT_STRIDE, opt, g.vza, g.sza, g.raa, fd);
+    rec[0 * L + line] = r.Kc;  rec[1 * L + line] = r.Kg;  rec[2 * L + line] = r.Kt;
+    rec[3 * L + line] = r.Kz;  rec[4 * L + line] = r.Kpg; rec[5 * L + line] = r.Kpz;
+    rec[6 * L + line] = r.q;   rec[7 * L + line] = r.fd;  rec[8 * L + line] = r.mus;
+    rec[9 * L + line] = r.t0;  rec[10 * L + line] = r.tp0; rec[11 * L + line] = r.pe_s;
+    rec[12 * L + line] = r.pn0_s;
+    if (kprop) {
+        kprop[4 * line + 0] = r.Kc; kprop[4 * line + 1] = r.Kg;
+        kprop[4 * line + 2] = r.Kt; kprop[4 * line + 3] = r.Kz;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+template <int LPT>
+__global__ void __launch_bounds__(128)
+rsurf_wide_kernel(int n_sets, int n_geom, int n_wl, int spectra_per_set, int tile_lines,
+                  const double* __restrict__ structure, const double* __restrict__ lut,
+                  const double* __restrict__ rec,
+                  const double* __restrict__ rleaf, const double* __restrict__ tleaf,
+                  const double* __restrict__ rsoil,
+                  double* __restrict__ rsurf, double* __restrict__ scomp)
+{
+    extern __shared__ double srec[];     // [GORT_REC_FIELDS - 1][tile_lines]
+    const long L = (long) n_sets * n_geom;
+    const long line0 = (long) blockIdx.x * tile_lines;
+    const int nl = (int) min((long) tile_lines, L - line0);
+    for (int i = threadIdx.x; i < nl * 12; i += blockDim.x) {
+        int f = i / nl, l = i - f * nl;
+        srec[f * tile_lines + l] = rec[(size_t) f * L + line0 + l];
+    }
+    __syncthreads();
+
+    const int w0 = blockIdx.y * (blockDim.x * LPT) + threadIdx.x;
+    int wj[LPT];
+#pragma unroll
+    for (int j = 0; j < LPT; j++) wj[j] = w0 + j * blockDim.x;
+    if (wj[0] >= n_wl) return;
+
+    Canopy c;
+    LeafTerms Lf[LPT];
+    SunTerms S[LPT];
+    int cur_set = -1;
+    double p_fd = 0, p_mus = 0, p_t0 = 0, p_tp0 = 0, p_pe = 0;
+    for (int l = 0; l < nl; l++) {
+        const long line = line0 + l;
+        const int m = (int) (line / n_geom);
+        bool fresh = (m != cur_set);
+        if (fresh) {
+            cur_set = m;
+            c = canopy_load(structure, n_sets, m, lut);
+            const size_t sb = spectra_per_set ? (size_t) m * n_wl : 0;
+#pragma unroll
+            for (int j = 0; j < LPT; j++) {
+                int w = min(wj[j], n_wl - 1);
+                Lf[j] = leaf_terms(c, rleaf[sb + w], tleaf[sb + w], rsoil[sb + w]);
+            }
+        }
+        const double fd = srec[7 * tile_lines + l], mus = srec[8 * tile_lines + l];
+        const double t0 = srec[9 * tile_lines + l], tp0 = srec[10 * tile_lines + l];
+        const double pe = srec[11 * tile_lines + l];
+        if (fresh || fd != p_fd || mus != p_mus || t0 != p_t0 || tp0 != p_tp0 || pe != p_pe) {
+            p_fd = fd; p_mus = mus; p_t0 = t0; p_tp0 = tp0; p_pe = pe;
+#pragma unroll
+            for (int j = 0; j < LPT; j++) S[j] = sun_terms(c, Lf[j], fd, mus, t0, tp0, pe);
+        }
+        const double Kc = srec[0 * tile_lines + l], Kg = srec[1 * tile_lines + l];
+        const double Kt = srec[2 * tile_lines + l], Kz = srec[3 * tile_lines + l];
+        const double Kpg = srec[4 * tile_lines + l], Kpz = srec[5 * tile_lines + l];
+        const double q = srec[6 * tile_lines + l];
+#pragma unroll
+        for (int j = 0; j < LPT; j++) {
+            double C;
+            double r = view_rsurf(c, Lf[j], S[j], fd, q, Kc, Kg, Kt, Kz, Kpg, Kpz, C);
+            if (wj[j] < n_wl) {
+                size_t o = (size_t) line * n_wl + wj[j];
+                rsurf[o] = r;
+                if (scomp) {
+                    double4 v = make_double4(C, S[j].G, S[j].T, S[j].Z);
+                    *reinterpret_cast<double4*>(scomp + 4 * o) = v;
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+rsurf_flat_kernel(int n_sets, int n_geom, int n_wl, int spectra_per_set,
+                  const double* __restrict__ structure, const double* __restrict__ lut,
+                  const double* __restrict__ rec,
+                  const double* __restrict__ rleaf, const double* __restrict__ tleaf,
+                  const double* __restrict__ rsoil,
+                  double* __restrict__ rsurf, double* __restrict__ scomp)
+{
+    const long L = (long) n_sets * n_geom;
+    const long total = L * n_wl;
+    long e = (long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= total) return;
+    const long line = e / n_wl;
+    const int w = (int) (e - line * n_wl);
+    const int m = (int) (line / n_geom);
+    Canopy c = canopy_load(structure, n_sets, m, lut);
+    const size_t sb = (spectra_per_set ? (size_t) m * n_wl : 0) + w;
+    LeafTerms Lf = leaf_terms(c, rleaf[sb], tleaf[sb], rsoil[sb]);
+    const double fd = rec[7 * L + line];
+    SunTerms S = sun_terms(c, Lf, fd, rec[8 * L + line], rec[9 * L + line], rec[10 * L + line], rec[11 * L + line]);
+    double C;
+    double r = view_rsurf(c, Lf, S, fd, rec[6 * L + line], rec[0 * L + line], rec[1 * L + line],
+                          rec[2 * L + line], rec[3 * L + line], rec[4 * L + line], rec[5 * L + line], C);
+    rsurf[e] = r;
+    if (scomp) *reinterpret_cast<double4*>(scomp + 4 * e) = make_double4(C, S.G, S.T, S.Z);
+}
+
+int launch_brdf(gort_ctx *ctx, cudaStream_t s, const gort_shape &sh, const double *structure,
+                const double *lut, const double *angles, const double *rleaf, const double *tleaf,
+                const double *rsoil, double *rsurf, double *scomp, double *kprop)
+{
+    if (sh.n_sets <= 0 || sh.n_geom <= 0 || sh.n_wl <= 0)
+        return set_error(ctx, GORT_ERR_INVALID, "gort_brdf: n_sets, n_geom and n_wl must be positive");
+    const long L = (long) sh.n_sets * sh.n_geom;
+    double *rec = (double *) workspace(ctx, sizeof(double) * GORT_REC_FIELDS * (size_t) L);
+    if (!rec) return GORT_ERR_NOMEM;
+    cudaEvent_t *ev = (ctx->prof_ev && ctx->prof_n < ctx->prof_cap) ? ctx->prof_ev + 3 * ctx->prof_n : NULL;
+    if (ev) cudaEventRecord(ev[0], s);
+    {
+        int threads = 128;
+        long blocks = (L + threads - 1) / threads;
+        geom_kernel<<<(unsigned) blocks, threads, 0, s>>>(sh.n_sets, sh.n_geom, sh.geom_per_set, sh.opt,
+                                                          structure, lut, angles, rec, kprop);
+        ctx->launches++;
+    }
+    if (ev) cudaEventRecord(ev[1], s);
+    if (sh.n_wl >= 64) {
+        const int threads = 128;
+        const int LPT = 2;
+        int tile = 32;
+        dim3 grid((unsigned) ((L + tile - 1) / tile), (unsigned) ((sh.n_wl + threads * LPT - 1) / (threads * LPT)));
+        size_t smem = sizeof(double) * 12 * tile;
+        rsurf_wide_kernel<LPT><<<grid, threads, smem, s>>>(sh.n_sets, sh.n_geom, sh.n_wl, sh.spectra_per_set, tile,
+                                                           structure, lut, rec, rleaf, tleaf, rsoil, rsurf, scomp);
+    } else {
+        const int threads = 128;
+        long total = L * sh.n_wl;
+        long blocks = (total + threads - 1) / threads;
+        rsurf_flat_kernel<<<(unsigned) blocks, threads, 0, s>>>(sh.n_sets, sh.n_geom, sh.n_wl, sh.spectra_per_set,
+                                                                structure, lut, rec, rleaf, tleaf, rsoil, rsurf, scomp);
+    }
+    ctx->launches++;
+    if (ev) { cudaEventRecord(ev[2], s); ctx->prof_n++; }
+    return check_cuda(ctx, cudaGetLastError(), "gort_brdf launch");
+}
+
+// ------------------------------------------------------------------------------------------------
+// Energy balance.  One CTA of 512 threads per (set, sun line).
+//   phase 1: thread n -> quadrature node (azimuth i = n % 32, zenith j = 16 + n / 32): geometry record
+//   phase 2: per wavelength chunk, threads compute the (sun, lambda) terms into shared memory
+//   phase 3: warp per wavelength, lane = azimuth node, 16 zenith nodes accumulated in the
+//            reference's order (gortt_albedo.c:101-130), azimuth sum by warp shuffle (:132-133)
+#define GORT_EN_THREADS 512
+#define GORT_EN_CHUNK 256
+
+__global__ void __launch_bounds__(GORT_EN_THREADS)
+energy_kernel(int n_sets, int n_geom, int n_wl, int geom_per_set, int spectra_per_set, gort_options opt,
+              const double* __restrict__ structure, const double* __restrict__ lut,
+              const double* __restrict__ angles, const double* __restrict__ gl /*[2][32]*/,
+              const double* __restrict__ rleaf, const double* __restrict__ tleaf,
+              const double* __restrict__ rsoil,
+              double* __restrict__ albedo, double* __restrict__ favegt, double* __restrict__ fasoil)
+{
+    __shared__ double nrec[7][GORT_EN_THREADS];         // Kc Kg Kt Kz Kpg Kpz q per node
+    __shared__ double sunv[6];                          // fd mus t0 tp0 pe_s pn0_s
+    __shared__ double lam[6][GORT_EN_CHUNK];            // A PD FCf G Z T per wavelength of the chunk
+    __shared__ double s_absc[GORT_NQUAD], s_wts[GORT_NQUAD];
+
+    const long L = (long) n_sets * n_geom;
+    const long line = blockIdx.x;
+    const int m = (int) (line / n_geom);
+    const long a = geom_per_set ? line : (line - (long) m * n_geom);
+    const long na = geom_per_set ? L : n_geom;
+    const int tid = threadIdx.x;
+    if (tid < GORT_NQUAD) { s_absc[tid] = gl[tid]; s_wts[tid] = gl[GORT_NQUAD + tid]; }
+    __syncthreads();
+
+    const Canopy c = canopy_load(structure, n_sets, m, lut);
+    const Line g = line_from_degrees(angles[0 * na + a], angles[1 * na + a], angles[2 * na + a], angles[3 * na + a]);
+    const double fd = opt.use_fd ? opt.fd : cos(g.sza) / (cos(g.sza) + 0.09);
+    const double xr = 0.5 * (1. + 1.), xm = 0.5 * (1. - 1.);                     // gortt_albedo.c:82-83
+    const double ym = 0.5 * (2. * GORT_PI - 0.), yr = 0.5 * (2. * GORT_PI + 0.);  // :84-85
+    {
+        const int i = tid & 31, j = GORT_NQUAD / 2 + (tid >> 5);
+        double y = ym + yr * s_absc[i];                                          // :91
+        double vaa = y;
+        for (int it = 0; it < 8 && vaa > 2 * GORT_PI; it++) vaa -= 2 * GORT_PI;  // :96
+        double raa = fold_raa(g.saa - vaa);                                      // :97-98
+        double x = xm + xr * s_absc[j];                                          // :103
+        double vza = acos(x);                                                    // :105
+        GeomRec r = geom_record(c, lut + (size_t) m * GORT_LUT_STRIDE, opt, vza, g.sza, raa, fd);
+        nrec[0][tid] = r.Kc; nrec[1][tid] = r.Kg; nrec[2][tid] = r.Kt; nrec[3][tid] = r.Kz;
+        nrec[4][tid] = r.Kpg; nrec[5][tid] = r.Kpz; nrec[6][tid] = r.q;
+        if (tid == 0) {
+            sunv[0] = r.fd; sunv[1] = r.mus; sunv[2] = r.t0; sunv[3] = r.tp0; sunv[4] = r.pe_s; sunv[5] = r.pn0_s;
+        }
+    }
+    __syncthreads();
+    const double mus = sunv[1], t0 = sunv[2], tp0 = sunv[3], pe = sunv[4], Pn0 = sunv[5];
+    const size_t sb = spectra_per_set ? (size_t) m * n_wl : 0;
+    const int lane = tid & 31, warp = tid >> 5;
+
+    for (int wbase = 0; wbase < n_wl; wbase += GORT_EN_CHUNK) {
+        const int nc = min(GORT_EN_CHUNK, n_wl - wbase);
+        __syncthreads();
+        if (tid < nc) {
+            const int w = wbase + tid;
+            LeafTerms Lf = leaf_terms(c, rleaf[sb + w], tleaf[sb + w], rsoil[sb + w]);
+            SunTerms S = sun_terms(c, Lf, fd, mus, t0, tp0, pe);
+            lam[0][tid] = Lf.A; lam[1][tid] = S.PD; lam[2][tid] = S.FCf;
+            lam[3][tid] = S.G; lam[4][tid] = S.Z; lam[5][tid] = S.T;
+        }
+        __syncthreads();
+        for (int k = warp; k < nc; k += GORT_EN_THREADS / 32) {
+            LeafTerms Lf; SunTerms S;
+            Lf.A = lam[0][k]; S.PD = lam[1][k]; S.FCf = lam[2][k]; S.G = lam[3][k]; S.Z = lam[4][k]; S.T = lam[5][k];
+            double sum_x = 0.;
+#pragma unroll 4
+            for (int jj = 0; jj < GORT_NQUAD / 2; jj++) {
+                const int n = jj * 32 + lane;
+                double C;
+                double r = view_rsurf(c, Lf, S, fd, nrec[6][n], nrec[0][n], nrec[1][n], nrec[2][n], nrec[3][n],
+                                      nrec[4][n], nrec[5][n], C);
+                const int j = GORT_NQUAD / 2 + jj;
+                double x = xm + xr * s_absc[j];
+                sum_x = sum_x + r * s_wts[j] * fabs(x) * xr;                     // :128-129
+            }
+            double v = sum_x * s_wts[lane] * yr;                                 // :132-133
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+            if (lane == 0) {
+                const int w = wbase + k;
+                const size_t o = (size_t) line * n_wl + w;
+                double alb = v / GORT_PI;                                        // :136
+                double rs = rsoil[sb + w];
+                double Fu2 = S.G * Pn0 + S.Z * (1. - Pn0);                       // gortt_albedo.c:48
+                double Fd2 = Pn0 + S.Z * (1. - Pn0) / rs;                        // :49
+                albedo[o] = alb;
+                favegt[o] = 1. - alb - Fd2 + Fu2;                                // :51
+                fasoil[o] = Fd2 - Fu2;                                           // :52
+            }
+        }
+    }
+}
+
+int launch_energy(gort_ctx *ctx, cudaStream_t s, const gort_shape &sh, const double *structure,
+                  const double *lut, const double *angles, const double *rleaf, const double *tleaf,
+                  const double *rsoil, double *albedo, double *favegt, double *fasoil)
+{
+    if (sh.n_sets <= 0 || sh.n_geom <= 0 || sh.n_wl <= 0)
+        return set_error(ctx, GORT_ERR_INVALID, "gort_energy: n_sets, n_geom and n_wl must be positive");
+    const long L = (long) sh.n_sets * sh.n_geom;
+    energy_kernel<<<(unsigned) L, GORT_EN_THREADS, 0, s>>>(sh.n_sets, sh.n_geom, sh.n_wl, sh.geom_per_set,
+                                                           sh.spectra_per_set, sh.opt, structure, lut, angles,
+                                                           ctx->d_gauleg, rleaf, tleaf, rsoil, albedo, favegt, fasoil);
+    ctx->launches++;
+    return check_cuda(ctx, cudaGetLastError(), "gort_energy launch");
+}
+
+// ------------------------------------------------------------------------------------------------
+// gauleg, gortt_albedo.c:141-199, n = 32 on (-1, 1).  One thread per root.
+__global__ void gauleg_kernel(double* __restrict__ out)
+{
+    const int n = GORT_NQUAD;
+    const double x1 = -1., x2 = 1.;
+    int i = threadIdx.x;
+    int mm = (n + 1) / 2;
+    if (i >= mm) return;
+    double xm = 0.5 * (x2 + x1), xl = 0.5 * (x2 - x1);
+    double z = cos(3.141592654 * (i + 0.75) / (n + 0.5)), z1, pp;
+    int guard = 0;
+    do {
+        double p1 = 1.0, p2 = 0.0, p3;
+        for (int j = 1; j <= n; j++) {
+            p3 = p2;
+            p2 = p1;
+            p1 = ((2.0 * j - 1.0) * z * p2 - (j - 1.0) * p3) / j;
+        }
+        pp = n * (z * p1 - p2) / (z * z - 1.0);
+        z1 = z;
+        z = z1 - p1 / pp;
+    } while (fabs(z - z1) > 3.0e-11 && ++guard < 100);
+    out[i] = xm - xl * z;
+    out[n - 1 - i] = xm + xl * z;
+    double w = 2.0 * xl / ((1.0 - z * z) * pp * pp);
+    out[n + i] = w;
+    out[n + n - 1 - i] = w;
+}
+
+int launch_gauleg(gort_ctx *ctx, cudaStream_t s, double *d_out)
+{
+    gauleg_kernel<<<1, 32, 0, s>>>(d_out);
+    ctx->launches++;
+    return check_cuda(ctx, cudaGetLastError(), "gauleg launch");
+}
+
+// ------------------------------------------------------------------------------------------------
+// FP64 FMA microbenchmark: the measured denominator for the FP64 roofline.
+__global__ void __launch_bounds__(256) dfma_kernel(double* out, int iters, double seed)
+{
+    double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 0.9999999, b = 1e-7;
+    for (int i = 0; i < iters; i++) {
+        a0 = fma(a0, m, b); a1 = fma(a1, m, b); a2 = fma(a2, m, b); a3 = fma(a3, m, b);
+        a4 = fma(a4, m, b); a5 = fma(a5, m, b); a6 = fma(a6, m, b); a7 = fma(a7, m, b);
+    }
+    out[(size_t) blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+int launch_dfma_peak(gort_ctx *ctx, cudaStream_t s, double *tflops)
+{
+    const int blocks = ctx->sm_count * 8, threads = 256, iters = 4096;
+    double *d = (double *) workspace(ctx, sizeof(double) * (size_t) blocks * threads);
+    if (!d) return GORT_ERR_NOMEM;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; rep++) {
+        cudaEventRecord(e0, s);
+        dfma_kernel<<<blocks, threads, 0, s>>>(d, iters, 1.0);
+        cudaEventRecord(e1, s);
+        cudaEventSynchronize(e1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && ms < best) best = ms;
+        ctx->launches++;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    double flops = 2.0 * 8.0 * iters * (double) blocks * threads;
+    *tflops = flops / (best * 1e-3) / 1e12;
+    return check_cuda(ctx, cudaGetLastError(), "dfma microbenchmark");
+}
+
+}  // namespace gort

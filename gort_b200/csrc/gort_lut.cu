@@ -1,0 +1,414 @@
+// gort_lut.cu -- KOpen / P(n) gap-probability LUT generation (sm_100a, FP64, -fmad=false).
+//
+// Replaces gortt_init_params (gortt.c:632-868) + gortt_gap_probabilities
+// (gortt_pn_kopen.c:7-129 and everything it calls, :134-924, :1083-1140) and
+// gortt_gap_probabilities_Q08 (gortt_pn_kopen.c:1144-1200), restricted to what reaches the
+// outputs: p_n0[0][t], epgap[0][t], k_open[0], k_openep[0].  The reference's
+// vb / fb / t_open / dt_open / dk_open tables are never read by the BRDF or albedo path and are
+// not computed.
+//
+// Mapping: one CTA per canopy parameter set, one thread per zenith index t (91 of 96 lanes):
+//   v_g[h][t] -> p_n0[h][t] (15 layers)  ->  p_s0  ->  E[S]  ->  for every entry height sp_i and
+//   crown count n: P(n | s'), within-crown path s and its histogram bin  ->  epgap[0][t];
+//   thread 0 then runs the trapezoid rule over theta in the reference's order.
+// The path-length histogram pd_s[0][t][bin] is not materialised: epgap[0][t] = sum over bins of
+// exp(-s_bin tau') pd_s[bin] is accumulated entry by entry with the entry's bin index, which is
+// the same sum in a different association (differences ~1e-16 relative).
+//
+// Parity hazards honoured: no FMA contraction (r*r - h2*h2 must be exactly
+// 0 when h2 == r), running-sum loop counters (z += dz_p, h += dh), (int)(s/ds + 0.5) binning,
+// the |a3| < 1e-10 clamp, float-typed Simpson factors.
+#include "gort_device.cuh"
+#include "gort_internal.h"
+
+namespace gort {
+
+#define LUT_THREADS 96
+#define LUT_MAXCROWNS 30
+#define LUT_NH_ES 20
+#define LUT_NOINT 20
+
+struct Crown {
+    double r, rr, rrr;
+    double h1_p, h2_p, z2_p, dz_p, ds, lv_p, tau_p;
+};
+
+struct Ang {            // trig of one theta_p
+    double th, s, c, t;  // angle, sin, cos, tan
+};
+
+// gortt_pn_kopen.c:285-305
+__device__ __forceinline__ double left_circle_area(double r, double x_cut)
+{
+    double area_tot = GORT_PI * r * r;
+    double ang_sector = acos(fabs(x_cut) / r) * 2.0;
+    double area_sector = area_tot * ang_sector / (2.0 * GORT_PI);
+    double area_triangle = fabs(x_cut) * sqrt(r * r - x_cut * x_cut);
+    if (x_cut > 0.0) return area_tot - (area_sector - area_triangle);
+    return area_sector - area_triangle;
+}
+
+// gortt_pn_kopen.c:309-323
+__device__ __forceinline__ double right_ellipse_area(double r, double b, double x_cut)
+{
+    double x_cut_p = x_cut / (b / r);
+    double a_p = GORT_PI * r * r;
+    a_p -= left_circle_area(r, x_cut_p);
+    return a_p * (b / r);
+}
+
+// gortt_pn_kopen.c:170-229 with the "weird" section :233-282 inlined
+__device__ double cross_section(const Crown& c, const Ang& a, double h, double z)
+{
+    if (z < h - c.r) return 0.0;
+    double h_low = h - c.r * a.s;
+    double h_high = h + c.r * a.s;
+    if (z <= h_low) {
+        double q = c.rr - (h - z) * (h - z);
+        double r_p = (q <= 0) ? 0 : sqrt(q);
+        return GORT_PI * r_p * r_p;
+    } else if (z > h_low && z < h_high) {
+        double zdiff = h - z;
+        double r_p = sqrt(c.rr - zdiff * zdiff);
+        double x_cc = zdiff * a.t;
+        double x_p = x_cc / (1.0 - a.c * a.c);
+        double a_cp = left_circle_area(r_p, x_p - x_cc);
+        double a_ep = right_ellipse_area(c.r, c.r * (1.0 / a.c), x_p);
+        return a_cp + a_ep;
+    }
+    return GORT_PI * c.rr * (1.0 / a.c);
+}
+
+// gortt_pn_kopen.c:149-167
+__device__ double proj_volume(const Crown& c, const Ang& a, double h)
+{
+    double vol = 0.0;
+    int guard = 0;
+    for (double z = c.h1_p + c.dz_p / 2.0; z <= c.h2_p && guard < 100000; z += c.dz_p, guard++)
+        vol += cross_section(c, a, h, z) * (c.dz_p);
+    return vol;
+}
+
+// gortt_pn_kopen.c:858-872
+__device__ __forceinline__ double triang_fcn(double x, double b, double r, double tan_the)
+{
+    double a1 = tan_the * (x - b);
+    double a2 = r * r - x * x;
+    double a3 = a2 - a1 * a1;
+    if (fabs(a3) < 0.0000000001) a3 = 0.0;
+    return 2.0 * a1 * sqrt(a3);
+}
+
+// gortt_pn_kopen.c:811-854
+__device__ double triang(double b, double r, const Ang& a)
+{
+    double sint = a.s, cost = a.c;
+    double a1 = r * r - b * b * sint * sint;
+    double x0 = b * (sint * sint) + sqrt(a1) * cost;
+    const int m = LUT_NOINT;
+    double h = .50 * (x0 - b) / (double) (float) m;
+    double sum1 = 0.0;
+    for (int i = 0; i < m; i++) sum1 += triang_fcn(b + (double) (float) (2 * i + 1) * h, b, r, a.t);
+    double volume = 4.0 * sum1;
+    double sum2 = 0.0;
+    for (int i = 0; i < m - 1; i++) sum2 += triang_fcn(b + (double) (float) (2 * (i + 1)) * h, b, r, a.t);
+    volume += 2.0 * sum2;
+    volume += triang_fcn(x0, b, r, a.t);
+    volume += triang_fcn(b, b, r, a.t);
+    volume *= h / 3.0;
+    return volume;
+}
+
+// gortt_pn_kopen.c:796-806
+__device__ __forceinline__ double sector(double a1, double a2, double r)
+{
+    double b1 = r * r * a1 - (a1 * a1 * a1) / 3.0;
+    double b2 = r * r * a2 - (a2 * a2 * a2) / 3.0;
+    return GORT_PI * (b2 - b1) / 2.0;
+}
+
+// gortt_pn_kopen.c:771-792
+__device__ double trisec(double hh, double hh_b, const Ang& a, double r)
+{
+    double tmp = (hh - hh_b);
+    double x = -1.0 * tmp * a.s + sqrt(r * r - tmp * tmp) * a.c;
+    double b = -tmp / a.s;
+    return triang(b, r, a) + sector(x, r, r);
+}
+
+// gortt_pn_kopen.c:876-886
+__device__ __forceinline__ double cylind_fcn(double x, double r)
+{
+    return .50 * x * sqrt(r * r - x * x) + .50 * r * r * asin(x / r);
+}
+
+// gortt_pn_kopen.c:891-924
+__device__ double cylind(double r, double h1, double h2, double h)
+{
+    double slope = h / (h2 - h1);
+    double tmp1 = sqrt(r * r - h1 * h1);
+    double tmp2 = sqrt(r * r - h2 * h2);
+    double volume = tmp1 * tmp1 * tmp1 - tmp2 * tmp2 * tmp2;
+    volume /= 3.0;
+    volume -= h1 * (cylind_fcn(h2, r) - cylind_fcn(h1, r));
+    volume *= 2.0 * slope;
+    if (h2 < r) {
+        double phi = acos(h2 / r);
+        double s1 = r * r * phi;
+        double s2 = r * sin(phi) * h2;
+        volume += (s1 - s2) * h;
+    }
+    return volume;
+}
+
+// gortt_pn_kopen.c:665-768; hp_h = height_p[h], hp_s = height_p[h_s]
+__device__ double tube_vol(const Crown& c, const Ang& a, double hp_h, double hp_s, double h_b)
+{
+    const double r = c.r;
+    double V, V_sp1, V_sp2, V_cyln, h_t, h_tt;
+    double tmp_s = (hp_s - hp_h) / a.c;
+    double V_0 = GORT_PI * c.rr * tmp_s;
+    V_0 += (4.0 / 3.0) * GORT_PI * c.rrr;
+
+    if ((hp_h - r) >= h_b) {
+        V = 0.0;
+    } else if ((hp_h - r * a.s) >= h_b) {
+        h_t = r - (hp_h - h_b);
+        V = (GORT_PI / 3.0) * h_t * h_t * (3.0 * r - h_t);
+    } else if ((hp_h + r * a.s) >= h_b) {
+        V_sp1 = (2.0 / 3.0) * GORT_PI * c.rrr;
+        V_sp1 -= trisec(hp_h, h_b, a, r);
+        h_tt = (h_b - (hp_h - r * a.s)) / a.c;
+        if (hp_s - r * a.s >= h_b) {
+            double hh1 = (hp_h - h_b) / a.s;
+            V_cyln = cylind(r, hh1, r, h_tt);
+            V_sp2 = 0.0;
+        } else {
+            double hh1 = (hp_h - h_b) / a.s;
+            double hh2 = (hp_s - h_b) / a.s;
+            double hh = (hp_s - hp_h) / a.c;
+            V_cyln = cylind(r, hh1, hh2, hh);
+            V_sp2 = trisec(h_b, hp_s, a, r);
+        }
+        V = V_sp1 + V_cyln + V_sp2;
+    } else if (hp_s - r * a.s >= h_b) {
+        double tmp_h = (h_b - hp_h) / a.c;
+        V_cyln = GORT_PI * r * r * tmp_h;
+        V_sp1 = (2.0 / 3.0) * GORT_PI * c.rrr;
+        V = V_sp1 + V_cyln;
+    } else if (hp_s + r * a.s >= h_b) {
+        h_tt = (hp_s + r * a.s - h_b) / a.c;
+        double hh1 = (h_b - hp_s) / a.s;
+        double tmp_h = (hp_s - hp_h) / a.c;
+        V_cyln = GORT_PI * r * r * tmp_h - cylind(r, hh1, r, h_tt);
+        V_sp2 = trisec(h_b, hp_s, a, r);
+        V_sp1 = (2.0 / 3.0) * GORT_PI * c.rrr;
+        V = V_cyln + V_sp2 + V_sp1;
+    } else if (hp_s + r >= h_b) {
+        h_t = r - (h_b - hp_s);
+        V_sp1 = (GORT_PI / 3.0) * h_t * h_t * (3.0 * r - h_t);
+        V = V_0 - V_sp1;
+    } else {
+        V = V_0;
+    }
+    return V;
+}
+
+// gortt_pn_kopen.c:566-645; hz = height_p[z]
+__device__ double mean_single_crown_path(const Crown& c, const Ang& a, double hz, double h)
+{
+    if (hz > h + c.r - 0.0001) return 0.0;
+    if (hz < h - c.r + 0.0001) return 4.0 * c.r / 3.0;
+    double V_sphere = 4.0 * GORT_PI * c.rrr / 3.0;
+    double zdiff = fabs(h - hz);
+    double ht = c.r - zdiff;
+    double V_slice = GORT_PI * ht * ht / 3.0 * (3.0 * c.r - ht);
+    double V_tot = (hz > h) ? V_slice : V_sphere - V_slice;
+    V_tot /= a.c;
+    double proj_area;
+    if (h < hz) proj_area = cross_section(c, a, h, (h - zdiff));
+    else proj_area = cross_section(c, a, h, (h + zdiff));
+    return V_tot / proj_area;
+}
+
+// gortt_pn_kopen.c:534-563
+__device__ double expected_single_crown_path(const Crown& c, const Ang& a, double hz)
+{
+    double ES = 0.0;
+    double dh = (c.h2_p - c.h1_p) / (double) LUT_NH_ES;
+    int guard = 0;
+    for (double h = c.h1_p + dh / 2.0; h <= c.h2_p && guard < 100000; h += dh, guard++)
+        ES += mean_single_crown_path(c, a, hz, h) * ((1.0 / (c.h2_p - c.h1_p)) * dh);
+    return ES;
+}
+
+__global__ void __launch_bounds__(LUT_THREADS)
+lut_full_kernel(int n_sets, const double* __restrict__ structure, double* __restrict__ lut)
+{
+    __shared__ double s_hp[GORT_NLAYERS];        // height_p
+    __shared__ double s_pn0[GORT_NTH];
+    __shared__ double s_epg[GORT_NTH];
+    __shared__ double s_sin2[GORT_NTH];
+    const int m = blockIdx.x;
+    const int t = threadIdx.x;
+
+    // ---- gortt_init_params, gortt.c:641-697 --------------------------------------------------
+    const double lambda = structure[0 * (size_t) n_sets + m];
+    const double r      = structure[1 * (size_t) n_sets + m];
+    const double b      = structure[2 * (size_t) n_sets + m];
+    const double h1     = structure[3 * (size_t) n_sets + m];
+    const double h2     = structure[4 * (size_t) n_sets + m];
+    const double favd   = structure[5 * (size_t) n_sets + m];
+    const double ellip = b / r;
+    Crown c;
+    c.r = r; c.rr = r * r; c.rrr = c.rr * r;
+    const double z1 = h1 - r * ellip;
+    const double z2 = h2 + r * ellip;
+    const double lv = lambda / (h2 - h1);
+    const double favd_p = favd * ellip;
+    c.tau_p = 0.5 * favd_p;
+    c.lv_p = lv * ellip;
+    c.z2_p = z2 / ellip;
+    c.h1_p = h1 / ellip;
+    c.h2_p = h2 / ellip;
+    const double dz = (double) (z2 - z1) / ((double) GORT_NLAYERS - 1.0);
+    c.ds = dz;
+    c.dz_p = dz / ellip;
+    if (t < GORT_NLAYERS) {                                                      // gortt.c:778-781
+        double height = z2 - dz * (double) (GORT_NLAYERS - 1 - t);
+        s_hp[t] = height / ellip;
+    }
+    __syncthreads();
+
+    const double dth = 1 * GORT_PI / 180.0;
+    double e_t = 0.0, pn0_0 = 0.0, theta = 0.0;
+    if (t < GORT_NTH) {
+        theta = dth * (double) t;                                                // gortt.c:783-797
+        if (theta >= GORT_PI / 2.0) theta = GORT_PI / 2.0 - 1.0 * GORT_PI / 180.0;
+        Ang a;
+        a.th = atan(tan(theta) * ellip);
+        if (a.th >= GORT_PI / 2.0) a.th = GORT_PI / 2.0 - 1.0 * GORT_PI / 180.0;
+        a.s = sin(a.th); a.c = cos(a.th); a.t = tan(a.th);
+
+        // ---- P(n=0), gortt_pn_kopen.c:24-32 ---------------------------------------------------
+        double pn0[GORT_NLAYERS];
+#pragma unroll 1
+        for (int h = 0; h < GORT_NLAYERS; h++) {
+            double vg = proj_volume(c, a, s_hp[h]);
+            pn0[h] = exp(-1.0 * c.lv_p * vg);
+        }
+        pn0_0 = pn0[0];
+
+        if (t < GORT_NTH - 1) {                                                  // :1099
+            const double hp0 = s_hp[0];
+            const double es = expected_single_crown_path(c, a, hp0);             // :445
+#pragma unroll 1
+            for (int sp_i = GORT_NLAYERS - 2; sp_i > 0; sp_i--) {                // :457 (sp_i = 14 adds p_s0 = 0)
+                const double hps = s_hp[sp_i];
+                const double s_p = (double) (hps - hp0) / a.c;                   // :464
+                const double P_s_p = pn0[sp_i + 1] - pn0[sp_i];                  // :43, :482
+                double temp1 = tube_vol(c, a, hp0, hps, c.h2_p) - tube_vol(c, a, hp0, hps, c.h1_p);   // :496
+                temp1 *= c.lv_p;                                                 // :497
+                const double E = exp(-temp1);
+                double pw = 1.0, fact = 1.0;
+#pragma unroll 1
+                for (int n = 1; n <= LUT_MAXCROWNS; n++) {                       // :489
+                    pw *= temp1;                                                 // temp1^n
+                    fact *= (double) n;                                          // gortt.c:752-754
+                    double P_n = (pw * E) / (fact * (1.0 - E));                  // :501-502
+                    double s = s_p * (1.0 - exp(-1.0 * (double) n * es / s_p));  // :508
+                    int idx = (int) (s / c.ds + 0.5);                            // :134-139, :522
+                    // gortt_calc_epgap + gortt_calc_pgap, :1110-1114, :1138
+                    e_t += exp(-((double) idx * c.ds) * c.tau_p) * (P_n * P_s_p);
+                }
+            }
+        }
+        s_pn0[t] = pn0_0;
+        s_epg[t] = e_t;
+        s_sin2[t] = sin(2.0 * theta);
+        double* o = lut + (size_t) m * GORT_LUT_STRIDE;
+        o[t] = pn0_0;
+        o[GORT_NTH + t] = e_t;
+    }
+    __syncthreads();
+
+    // ---- gortt_calc_kopen, gortt_pn_kopen.c:351-375 for h = 0, sequential like the reference ----
+    if (t == 0) {
+        double ko = 0.0, ke = 0.0;
+        double tmp1_last = s_pn0[0] * s_sin2[0];
+        double tmp2_last = s_epg[0] * s_sin2[0];
+        for (int i = 1; i < GORT_NTH; i++) {
+            double tmp1 = s_pn0[i] * s_sin2[i];
+            ko += (tmp1 + tmp1_last) / 2.0 * dth;
+            tmp1_last = tmp1;
+            double tmp2 = s_epg[i] * s_sin2[i];
+            ke += (tmp2 + tmp2_last) / 2.0 * dth;
+            tmp2_last = tmp2;
+        }
+        double* o = lut + (size_t) m * GORT_LUT_STRIDE;
+        o[2 * GORT_NTH] = ko;
+        o[2 * GORT_NTH + 1] = ke;
+    }
+}
+
+// gortt_pn_kopen.c:1144-1200
+__global__ void __launch_bounds__(LUT_THREADS)
+lut_q08_kernel(int n_sets, const double* __restrict__ structure, double* __restrict__ lut)
+{
+    __shared__ double s_pn0[GORT_NTH];
+    __shared__ double s_epg[GORT_NTH];
+    __shared__ double s_sin2[GORT_NTH];
+    const int m = blockIdx.x;
+    const int t = threadIdx.x;
+    const double lambda = structure[0 * (size_t) n_sets + m];
+    const double r      = structure[1 * (size_t) n_sets + m];
+    const double b      = structure[2 * (size_t) n_sets + m];
+    const double favd   = structure[5 * (size_t) n_sets + m];
+    const double ellip = b / r;
+    const double rr = r * r;
+    const double dth = 1 * GORT_PI / 180.0;
+    if (t < GORT_NTH) {
+        double theta = dth * (double) t;
+        if (theta >= GORT_PI / 2.0) theta = GORT_PI / 2.0 - 1.0 * GORT_PI / 180.0;
+        double theta_p = atan(tan(theta) * ellip);
+        if (theta_p >= GORT_PI / 2.0) theta_p = GORT_PI / 2.0 - 1.0 * GORT_PI / 180.0;
+        double cc = GORT_PI * rr * lambda;                               // :1164
+        double l = favd * b * 4. / 3. * cc;                              // :1166
+        double k2 = 0.348535 * pow(cc, (-1.08069 - 0.0874595 * cc));     // :1168
+        double k1 = 0.0014166;
+        double a = cc * (exp(k1 * cc * cc) - exp(-k2 * l));              // :1171
+        double pn0 = exp(-cc / (cos(theta_p)));                          // :1185
+        double epg = exp(-a / (cos(theta_p))) - pn0;                     // :1186
+        s_pn0[t] = pn0; s_epg[t] = epg; s_sin2[t] = sin(2.0 * theta);
+        double* o = lut + (size_t) m * GORT_LUT_STRIDE;
+        o[t] = pn0;
+        o[GORT_NTH + t] = epg;
+    }
+    __syncthreads();
+    if (t == 0) {
+        double ko = 0.0, ke = 0.0;
+        // :1176-1177 read rows that are still calloc'd zeros
+        double tmp1_last = 0.0 * s_sin2[0], tmp2_last = 0.0 * s_sin2[0];
+        for (int i = 1; i < GORT_NTH; i++) {
+            double tmp1 = s_pn0[i] * s_sin2[i];
+            ko += (tmp1 + tmp1_last) / 2.0 * dth;
+            tmp1_last = tmp1;
+            double tmp2 = s_epg[i] * s_sin2[i];
+            ke += (tmp2 + tmp2_last) / 2.0 * dth;
+            tmp2_last = tmp2;
+        }
+        double* o = lut + (size_t) m * GORT_LUT_STRIDE;
+        o[2 * GORT_NTH] = ko;
+        o[2 * GORT_NTH + 1] = ke;
+    }
+}
+
+int launch_lut(gort_ctx *ctx, cudaStream_t s, int n_sets, const double *structure, int method, double *lut)
+{
+    if (method == GORT_LUT_Q08) lut_q08_kernel<<<n_sets, LUT_THREADS, 0, s>>>(n_sets, structure, lut);
+    else lut_full_kernel<<<n_sets, LUT_THREADS, 0, s>>>(n_sets, structure, lut);
+    ctx->launches++;
+    return check_cuda(ctx, cudaGetLastError(), "gort_lut launch");
+}
+
+}  // namespace gort

@@ -1,0 +1,159 @@
+/* gort_b200.h -- C ABI of the B200-native GORT forward operator.
+ *
+ * The reference (tquaife/gort) has no plugin / FFI interface: its hot path sits behind the C
+ * prototypes of include/gortt.h:216-277, called only from main() (gortt.c:108-120, :224-227,
+ * :294-295, :322) with three mutable structs.  This header is the batched, re-entrant
+ * replacement for exactly those prototypes.  Each entry point names the reference interface
+ * it replaces.  Plain C types only: pointers, sizes, POD structs.
+ *
+ * Conventions
+ *   - All arrays are FP64, structure-of-arrays, row-major, last index fastest.
+ *   - "structure" is [6][n_sets]: rows lambda, r, b, h1, h2, favd  (gortt_parameters fields set
+ *     by gortt.c:67-72 / gortt_cl_parser gortt.c:1026-1131).
+ *   - "angles" is [4][n_lines]: rows vza, vaa, sza, saa in DEGREES, i.e. the columns of the
+ *     reference's angles.dat (gortt.c:234, :1148).
+ *   - a LUT record is GORT_LUT_STRIDE doubles: p_n0[0][0..90], epgap[0][0..90], k_open[0],
+ *     k_openep[0] -- the only gap-probability results the BRDF reads (gortt.c:124-126,
+ *     :896-910, :492-525).  The "-W"/"-P" text file holds rows 0..89 and the k_open pair.
+ *   - Functions without a _dev suffix take HOST pointers: they copy inputs to the GPU, run the
+ *     CUDA kernels and copy results back before returning.  _dev functions take DEVICE
+ *     pointers, enqueue on `stream` (a cudaStream_t passed as void*, NULL = the context's own
+ *     stream) and return without synchronising.
+ *   - Every function returns GORT_OK or an error code; gort_last_error() gives the message.
+ *     The reference convention (print to stderr, exit(EXIT_FAILURE)) is kept by the gortt CLI,
+ *     not by the library.
+ *   - There is no CPU fallback: without a CUDA device gort_create() fails.
+ */
+#ifndef GORT_B200_H
+#define GORT_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GORT_NTH 91                         /* gortt.c:714 with dth = 1 degree */
+#define GORT_NLAYERS 15                     /* gortt.c:78 */
+#define GORT_LUT_STRIDE (2 * GORT_NTH + 2)  /* 184 doubles per parameter set */
+#define GORT_LUT_FILE_ROWS 90               /* gortt.c:124 */
+#define GORT_NQUAD 32                       /* gortt.c:93 npoints */
+#define GORT_WL_MIN 400.0                   /* gortt.c:1299, :1350 */
+#define GORT_WL_MAX 2500.0
+
+enum {
+    GORT_OK = 0,
+    GORT_ERR_INVALID = 1,   /* bad argument */
+    GORT_ERR_CUDA = 2,      /* CUDA runtime / launch failure, or no device */
+    GORT_ERR_RANGE = 3,     /* wavelength outside 400-2500 nm (gortt.c:1299-1302, :1350-1353) */
+    GORT_ERR_NOMEM = 4,
+    GORT_ERR_IO = 5
+};
+
+enum { GORT_LUT_FULL = 0, GORT_LUT_Q08 = 1 };   /* gortt.c:116-120 */
+
+typedef struct gort_ctx gort_ctx;
+
+/* Run-time options of the BRDF path that the reference keeps in gortt_parameters:
+ * -beta (gortt.c:1039, gortt_brdf.c:157) and -diffuse (gortt.c:1041, :290-291). */
+typedef struct {
+    int use_beta;
+    double beta;
+    int use_fd;
+    double fd;      /* already 1 - arg, as the reference stores it */
+} gort_options;
+
+/* Shape of one batched BRDF / energy call. */
+typedef struct {
+    int n_sets;            /* M canopy parameter sets */
+    int n_geom;            /* G input lines per set */
+    int n_wl;              /* W wavelengths */
+    int geom_per_set;      /* 0: angles is [4][G], shared by all sets; 1: [4][M*G], set-major */
+    int spectra_per_set;   /* 0: rleaf/tleaf/rsoil are [W]; 1: [M][W] */
+    gort_options opt;
+} gort_shape;
+
+/* ---- context ---------------------------------------------------------------------------- */
+int gort_create(int device, gort_ctx **out);
+void gort_destroy(gort_ctx *ctx);
+const char *gort_last_error(const gort_ctx *ctx);      /* ctx may be NULL: creation errors */
+void *gort_stream(gort_ctx *ctx);                       /* the context's cudaStream_t */
+int gort_synchronize(gort_ctx *ctx);
+int gort_device_count(void);
+/* pinned host memory for fast H2D/D2H through the host-pointer entry points */
+void *gort_host_alloc(size_t bytes);
+void gort_host_free(void *p);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+long gort_launch_count(const gort_ctx *ctx);
+
+/* ---- gap probabilities: replaces gortt_init_params + gortt_gap_probabilities /
+ *      gortt_gap_probabilities_Q08 (include/gortt.h:217,251; gortt.c:108-120) ------------- */
+int gort_lut_batch(gort_ctx *ctx, int n_sets, const double *structure, int method, double *lut);
+int gort_lut_batch_dev(gort_ctx *ctx, void *stream, int n_sets, const double *structure,
+                       int method, double *lut);
+
+/* ---- spectra: replaces gortt_price_soil + gortt_prospect_interface + prospect_DB_
+ *      (include/gortt.h:289-292; gortt.c:224-227).
+ *      leaf is [7][M] rows N,Cab,Car,Anth,Cbrown,Cw,Cm; soil is [4][M] rows rsl1..4.
+ *      user_leaf >= 0 is "-alb_leaf" (gortt.c:1355-1357), user_soil >= 0 is "-alb_soil"
+ *      (gortt.c:1305-1307); pass a negative value for "not set".
+ *      Outputs are [M][W]. ------------------------------------------------------------------ */
+int gort_spectra_batch(gort_ctx *ctx, int n_sets, const double *leaf, const double *soil,
+                       double user_leaf, double user_soil, int n_wl, const double *wavelength,
+                       double *rleaf, double *tleaf, double *rsoil);
+int gort_spectra_batch_dev(gort_ctx *ctx, void *stream, int n_sets, const double *leaf,
+                           const double *soil, double user_leaf, double user_soil, int n_wl,
+                           const double *wavelength, double *rleaf, double *tleaf, double *rsoil);
+/* the full 2101-band PROSPECT-D output of prospect_DB_ (prospect_DB.f90:72): refl, tran [M][2101] */
+int gort_prospect_batch(gort_ctx *ctx, int n_sets, const double *leaf, double *refl, double *tran);
+
+/* ---- BRDF: replaces the per-line block of main (gortt.c:240-295):
+ *      angle normalisation, gortt_prime_theta, fd, gortt_set_zenith_dependant_probabilities,
+ *      gortt_rsurf (include/gortt.h:216-219).
+ *      rsurf [M][G][W]; scomp (optional, may be NULL) [M][G][W][4] = C,G,T,Z (gortt.c:562-565);
+ *      kprop (optional) [M][G][4] = Kc,Kg,Kt,Kz (gortt.c:570-573). -------------------------- */
+int gort_brdf_batch(gort_ctx *ctx, const gort_shape *shape, const double *structure,
+                    const double *lut, const double *angles,
+                    const double *rleaf, const double *tleaf, const double *rsoil,
+                    double *rsurf, double *scomp, double *kprop);
+int gort_brdf_batch_dev(gort_ctx *ctx, void *stream, const gort_shape *shape,
+                        const double *structure, const double *lut, const double *angles,
+                        const double *rleaf, const double *tleaf, const double *rsoil,
+                        double *rsurf, double *scomp, double *kprop);
+
+/* ---- energy balance: replaces gortt_energy / gortt_albedo / gauleg (include/gortt.h:273-275;
+ *      gortt.c:208-209, :322).  One result per input line (only sza/saa of the line matter):
+ *      albedo, favegt, fasoil are [M][G][W]. ---------------------------------------------- */
+int gort_energy_batch(gort_ctx *ctx, const gort_shape *shape, const double *structure,
+                      const double *lut, const double *angles,
+                      const double *rleaf, const double *tleaf, const double *rsoil,
+                      double *albedo, double *favegt, double *fasoil);
+int gort_energy_batch_dev(gort_ctx *ctx, void *stream, const gort_shape *shape,
+                          const double *structure, const double *lut, const double *angles,
+                          const double *rleaf, const double *tleaf, const double *rsoil,
+                          double *albedo, double *favegt, double *fasoil);
+/* the 32-point Gauss-Legendre rule the energy path uses (gauleg, gortt_albedo.c:142-198) */
+int gort_gauleg(gort_ctx *ctx, double *abscissa, double *weights);
+
+/* ---- LUT text layout ("-W" / "-P", gortt.c:123-146) -- host-side formatting only --------- */
+/* writes 90 rows "%d %0.40f %0.40f\n" and the "-1" row for one LUT record; returns bytes
+ * written or a negative GORT_ERR_*.  fp is a FILE*. */
+long gort_lut_write_text(const double *lut, void *fp);
+/* fscanf("%d %lf %lf") loop into a LUT record that the caller has pre-filled (the reference
+ * reads over whatever gortt_init_params left: zeros) */
+int gort_lut_read_text(const char *path, double *lut);
+
+/* ---- measurement helpers --------------------------------------------------------------- */
+/* FP64 FMA peak of this device, measured with a register-resident DFMA loop (TFLOP/s) */
+int gort_dfma_peak(gort_ctx *ctx, double *tflops);
+/* Per-kernel device timing of the BRDF path with CUDA events recorded on the launching stream.
+ * gort_profile_begin arms up to max_steps BRDF calls; each armed gort_brdf_batch[_dev] records
+ * events around its geometry kernel and its per-wavelength kernel.  gort_profile_end synchronises,
+ * disarms and returns the mean milliseconds per call of each kernel over the recorded calls. */
+int gort_profile_begin(gort_ctx *ctx, int max_steps);
+int gort_profile_end(gort_ctx *ctx, double *geom_ms, double *rsurf_ms, int *n_steps);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GORT_B200_H */

@@ -131,6 +131,46 @@ def oracle():
     return _cache["oracle"]
 
 
+class UlpOracle(Checker):
+    """The oracle restatement linked against a 1-ULP-noisy libm (oracle/ulp_libm_shim.c)."""
+
+    def __init__(self, lib):
+        super().__init__(lib, "gort_oracle_")
+        lib.gort_oracle_ulp_seed.argtypes = [C.c_uint64]
+
+    def seed(self, s):
+        self.lib.gort_oracle_ulp_seed(s)
+
+
+def oracle_ulp():
+    if "ulp" not in _cache:
+        so = ROOT / "oracle" / "libgort_oracle_ulp.so"
+        if not so.exists():
+            build_checkers()
+        _cache["ulp"] = UlpOracle(C.CDLL(str(so)))
+    return _cache["ulp"]
+
+
+def sensitivity(fn, ref_value, seeds=(1, 2, 3)):
+    """Element-wise max |f_ulp(seed) - ref| over a few seeds: how far the reference algorithm itself
+    moves under a 1-ULP libm.  `fn(checker)` must return an array (or tuple of arrays) like ref_value."""
+    u = oracle_ulp()
+    single = not isinstance(ref_value, tuple)
+    refs = (ref_value,) if single else ref_value
+    sens = [np.zeros_like(np.asarray(r, dtype=np.float64)) for r in refs]
+    for sd in seeds:
+        u.seed(sd)
+        out = fn(u)
+        outs = (out,) if single else out
+        for k, (a, r) in enumerate(zip(outs, refs)):
+            if r is None:
+                continue
+            d = np.abs(np.asarray(a) - np.asarray(r))
+            d = np.where(np.isnan(d), np.inf, d)
+            sens[k] = np.maximum(sens[k], d)
+    return sens[0] if single else tuple(sens)
+
+
 def ref():
     if "ref" not in _cache:
         so = ROOT / "oracle" / "_ref" / "libgortt_ref.so"

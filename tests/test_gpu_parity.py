@@ -1,0 +1,294 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the oracle on the same seeded
+inputs.  Tolerance (BASELINE.json north_star / SURVEY.md 8d):
+        |x - ref| <= 1e-9 * max(|ref|, 1e-12),  NaN positions must coincide.
+"""
+import numpy as np
+import pytest
+
+from gort_b200 import workloads as wk
+import gort_b200
+from checkers import sensitivity
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-9
+FLOOR = 1e-12
+
+
+def rel_err(x, ref):
+    x = np.asarray(x); ref = np.asarray(ref)
+    assert x.shape == ref.shape, (x.shape, ref.shape)
+    nx, nr = np.isnan(x), np.isnan(ref)
+    assert np.array_equal(nx, nr), "NaN positions differ: %d vs %d" % (nx.sum(), nr.sum())
+    ok = ~nr
+    if not ok.any():
+        return 0.0
+    return float(np.max(np.abs(x[ok] - ref[ok]) / np.maximum(np.abs(ref[ok]), FLOOR)))
+
+
+def assert_close(x, ref, what, rtol=RTOL):
+    e = rel_err(x, ref)
+    assert e <= rtol, "%s: max rel err %.3e > %.1e" % (what, e, rtol)
+    return e
+
+
+COND_FACTOR = 32.0
+
+
+def assert_close_cond(x, ref, sens, what, rtol=RTOL):
+    """Strict bound first.  An entry that misses it must be explained by the reference algorithm's own
+    conditioning: |x - ref| <= COND_FACTOR * (how far the oracle itself moves under a 1-ULP libm,
+    tests/checkers.py:sensitivity).  Returns (strict worst rel err, number of entries excused)."""
+    x = np.asarray(x); ref = np.asarray(ref)
+    nx, nr = np.isnan(x), np.isnan(ref)
+    assert np.array_equal(nx, nr), "%s: NaN positions differ" % what
+    ok = ~nr
+    err = np.abs(x[ok] - ref[ok])
+    strict = err <= rtol * np.maximum(np.abs(ref[ok]), FLOOR)
+    excused = ~strict & (err <= COND_FACTOR * sens[ok])
+    bad = ~strict & ~excused
+    rel = err / np.maximum(np.abs(ref[ok]), FLOOR)
+    assert not bad.any(), "%s: %d entries miss 1e-9 and are not explained by conditioning; worst rel %.3e (sens %.3e, err %.3e)" % (
+        what, bad.sum(), rel[bad].max(), sens[ok][bad][rel[bad].argmax()], err[bad][rel[bad].argmax()])
+    return (float(rel.max()) if rel.size else 0.0), int(excused.sum())
+
+
+# ---------------------------------------------------------------------------------------------
+def test_c1_readme_end_to_end(gort, oracle):
+    w = wk.c1_readme()
+    st = w["structure"]
+    lut = gort.lut(st)
+    lut_o = oracle.lut(st[:, 0])
+    assert_close(lut[0], lut_o, "lut")
+    rl, tl, rs = gort.spectra(w["leaf"], w["soil"], w["wavelength"])
+    rl_o, tl_o, rs_o = oracle.spectra(w["leaf"][:, 0], w["soil"][:, 0], w["wavelength"])
+    assert_close(rl[0], rl_o, "rleaf"); assert_close(tl[0], tl_o, "tleaf"); assert_close(rs[0], rs_o, "rsoil")
+    rsurf, scomp, kprop = gort.brdf(st, lut, w["angles"], rl[0], tl[0], rs[0], want_scomp=True, want_kprop=True)
+    r_o, s_o, k_o = oracle.brdf(st[:, 0], lut_o, w["angles"].T, rl_o, tl_o, rs_o)
+    assert_close(rsurf[0], r_o, "rsurf"); assert_close(scomp[0], s_o, "scomp"); assert_close(kprop[0], k_o, "kprop")
+
+
+def test_golden_e1_alb_leaf(gort):
+    """-LAI 4.0 -alb_leaf 0.5, full-precision values captured from the reference."""
+    st = gort_b200.structure_from_options(lai=4.0).reshape(6, 1)
+    wl = np.array([450.0, 600.0, 800.0, 1000.0])
+    lut = gort.lut(st)
+    rl, tl, rs = gort.spectra(None, wk.DEFAULT_SOIL.reshape(4, 1), wl, user_leaf=0.5)
+    rsurf, kprop = gort.brdf(st, lut, np.array([[10.0], [0.0], [30.0], [20.0]]), rl[0], tl[0], rs[0], want_kprop=True)
+    gold = np.array([0.050996023726925049, 0.056904932488151413, 0.063793005449302428, 0.068538876965779413])
+    assert_close(rsurf[0, 0], gold, "E1 rsurf")
+    assert_close(kprop[0, 0], np.array([0.24500453130170924, 0.078537903246602814, 0.33486586946440577,
+                                        0.34159169598728212]), "E1 K")
+    alb, fv, fs = gort.energy(st, lut, np.array([[10.0], [0.0], [30.0], [20.0]]), rl[0], tl[0], rs[0])
+    assert_close(np.array([alb[0, 0, 0], fv[0, 0, 0], fs[0, 0, 0]]),
+                 np.array([0.063777031489123184, 0.68728814305278241, 0.24893482545809434]), "E1 energy")
+
+
+def test_golden_e4_lut_rows(gort):
+    st = gort_b200.structure_from_options(lai=4.0).reshape(6, 1)
+    lut = gort.lut(st)[0]
+    assert_close(np.array([lut[0], lut[91], lut[30], lut[91 + 30], lut[60], lut[91 + 60], lut[182], lut[183]]),
+                 np.array([0.4827649653877204, 0.049784714005155141, 0.18980914239271468, 0.054402229555638691,
+                           0.010675513076152983, 0.017277579752321828, 0.11690037154524389, 0.0348709390952388]),
+                 "E4 LUT rows")
+
+
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("method", [gort_b200.LUT_FULL, gort_b200.LUT_Q08])
+def test_lut_random_structures(gort, oracle, method):
+    rng = np.random.Generator(np.random.PCG64(11))
+    st = wk.random_structures(rng, 48)
+    lut = gort.lut(st, method)
+    worst, excused = 0.0, 0
+    for m in range(st.shape[1]):
+        lo = oracle.lut(st[:, m], method)
+        sens = sensitivity(lambda c: c.lut(st[:, m], method), lo)
+        e, n = assert_close_cond(lut[m], lo, sens, "lut set %d %r" % (m, st[:, m]))
+        worst = max(worst, e); excused += n
+    print("lut method %d: worst strict rel err %.3e, %d of %d entries excused by conditioning" % (
+        method, worst, excused, lut.size))
+
+
+def test_lut_c5_grid_corners(gort, oracle):
+    """corners + a stride through the C5 structural grid (extreme crown shapes)."""
+    st = wk.c5_lut_grid()["structure"]
+    idx = np.unique(np.concatenate([np.arange(0, st.shape[1], 4099), [0, st.shape[1] - 1]]))
+    sub = np.ascontiguousarray(st[:, idx])
+    lut = gort.lut(sub)
+    for k in range(sub.shape[1]):
+        assert_close(lut[k], oracle.lut(sub[:, k]), "C5 grid point %d %r" % (idx[k], sub[:, k]))
+
+
+def test_spectra_prospect_price(gort, oracle):
+    rng = np.random.Generator(np.random.PCG64(12))
+    leaf = wk.random_leaves(rng, 16)
+    soil = np.stack([rng.uniform(0.05, 0.4, 16), rng.uniform(-0.1, 0.1, 16), rng.uniform(-0.05, 0.05, 16),
+                     rng.uniform(-0.04, 0.04, 16)])
+    wl = np.concatenate([np.array([400.0, 2500.0, 858.5, 469.25, 1240.75, 2499.999]), rng.uniform(400, 2500, 40),
+                         wk.MODIS_BANDS])
+    rl, tl, rs = gort.spectra(leaf, soil, wl)
+    for m in range(16):
+        rl_o, tl_o, rs_o = oracle.spectra(leaf[:, m], soil[:, m], wl)
+        assert_close(rl[m], rl_o, "rleaf"); assert_close(tl[m], tl_o, "tleaf"); assert_close(rs[m], rs_o, "rsoil")
+    # full 2101-band table
+    r, t = gort.prospect(leaf[:, :3])
+    for m in range(3):
+        rl_o, tl_o, _ = oracle.spectra(leaf[:, m], soil[:, m], np.arange(400.0, 2501.0))
+        assert_close(r[m], rl_o, "prospect refl"); assert_close(t[m], tl_o, "prospect tran")
+    # user overrides (-alb_leaf / -alb_soil)
+    rl, tl, rs = gort.spectra(None, None, wl, user_leaf=0.5, user_soil=0.2, n_sets=2)
+    assert np.all(rl == 0.25) and np.all(tl == 0.25) and np.all(rs == 0.2)
+
+
+def test_spectra_wavelength_out_of_range(gort):
+    with pytest.raises(gort_b200.GortError) as ei:
+        gort.spectra(wk.DEFAULT_LEAF.reshape(7, 1), wk.DEFAULT_SOIL.reshape(4, 1), np.array([399.0, 500.0]))
+    assert ei.value.code == 3
+
+
+# ---------------------------------------------------------------------------------------------
+def _spectra_for(oracle, leaf, soil, wl):
+    return oracle.spectra(leaf, soil, wl)
+
+
+@pytest.mark.parametrize("nw", [7, 211])
+def test_brdf_random_shared_geometry(gort, oracle, nw):
+    """wide (W >= 64) and flat (W < 64) kernels; LUT from the oracle so only the BRDF path is compared."""
+    rng = np.random.Generator(np.random.PCG64(13 + nw))
+    M, G = 5, 97
+    st = wk.random_structures(rng, M)
+    leaf = wk.random_leaves(rng, M)
+    wl = wk.MODIS_BANDS if nw == 7 else np.arange(400.0, 2501.0, 10.0)
+    ang = np.stack([rng.uniform(-80, 89, G), rng.uniform(-400, 400, G), rng.uniform(-80, 89, G), rng.uniform(-400, 400, G)])
+    ang[2, 10:40] = 35.0; ang[3, 10:40] = 100.0            # a run of lines sharing the sun (cached sun terms)
+    ang[:, 0] = [0.0, 0.0, 0.0, 0.0]                       # nadir / overhead sun: beta = 0 branch
+    lut = np.stack([oracle.lut(st[:, m]) for m in range(M)])
+    sp = [oracle.spectra(leaf[:, m], wk.DEFAULT_SOIL, wl) for m in range(M)]
+    rl = np.stack([s[0] for s in sp]); tl = np.stack([s[1] for s in sp]); rs = np.stack([s[2] for s in sp])
+    rsurf, scomp, kprop = gort.brdf(st, lut, ang, rl, tl, rs, want_scomp=True, want_kprop=True)
+    for m in range(M):
+        r_o, s_o, k_o = oracle.brdf(st[:, m], lut[m], ang.T, rl[m], tl[m], rs[m])
+        assert_close(rsurf[m], r_o, "rsurf set %d" % m)
+        assert_close(scomp[m], s_o, "scomp set %d" % m)
+        # Kt = max(0, 1 - Kc - Kz - Kg) is a difference of O(1) areal proportions: conditioning-aware
+        ks = sensitivity(lambda c: c.brdf(st[:, m], lut[m], ang.T, rl[m], tl[m], rs[m])[2], k_o)
+        assert_close_cond(kprop[m], k_o, ks, "kprop set %d" % m)
+    # shared spectra + options (-beta, -diffuse)
+    rsurf = gort.brdf(st, lut, ang, rl[0], tl[0], rs[0], beta=0.3, fd=0.8)
+    for m in range(M):
+        r_o, _, _ = oracle.brdf(st[:, m], lut[m], ang.T, rl[0], tl[0], rs[0], beta=0.3, fd=0.8)
+        assert_close(rsurf[m], r_o, "rsurf(opt) set %d" % m)
+
+
+def test_brdf_per_set_geometry_c4_sample(gort, oracle):
+    w = wk.c4_enkf(n_members=64, seed=1002)
+    st, ang, wl = w["structure"], w["angles"], w["wavelength"]
+    M = st.shape[1]
+    lut = gort.lut(st)
+    rl, tl, rs = gort.spectra(w["leaf"], w["soil"], wl)
+    rsurf = gort.brdf(st, lut, ang, rl, tl, rs)
+    worst = 0.0
+    for m in range(M):
+        lut_o = oracle.lut(st[:, m])
+        sp = oracle.spectra(w["leaf"][:, m], w["soil"][:, m], wl)
+        r_o, _, _ = oracle.brdf(st[:, m], lut_o, ang[:, m, :].T, *sp)
+        worst = max(worst, assert_close(rsurf[m], r_o, "C4 member %d" % m))
+    print("C4 sample worst rel err %.3e" % worst)
+
+
+def test_brdf_grazing_nan_parity(gort, oracle):
+    """zenith > 89 deg: epgap row 90 is 0 -> -log(0) in the hotspot -> the reference yields NaN / Inf
+    by design; positions must coincide."""
+    st = gort_b200.structure_from_options(lai=4.0)
+    lut = oracle.lut(st)
+    wl = np.array([450.0, 800.0])
+    rl, tl, rs = oracle.spectra(wk.DEFAULT_LEAF, wk.DEFAULT_SOIL, wl)
+    ang = np.array([[89.5, 10.0, 30.0, 89.9], [0.0, 20.0, 0.0, 0.0], [30.0, 89.7, 89.2, 10.0], [0.0, 0.0, 180.0, 90.0]])
+    rsurf = gort.brdf(st.reshape(6, 1), lut.reshape(1, -1), ang, rl, tl, rs)
+    r_o, _, _ = oracle.brdf(st, lut, ang.T, rl, tl, rs)
+    assert np.array_equal(np.isnan(rsurf[0]), np.isnan(r_o))
+    assert_close(rsurf[0], r_o, "grazing")
+
+
+def test_brdf_q08_lut_and_read_lut(gort, oracle, tmp_path):
+    """E2: -q08_pn_kopen; and a "-P" LUT (rows 0..89 only, row 90 = 0) through the text layout."""
+    st = gort_b200.structure_from_options(lai=4.0)
+    wl = np.array([450.0, 600.0, 800.0, 1000.0])
+    lut = gort.lut(st.reshape(6, 1), gort_b200.LUT_Q08)
+    rl, tl, rs = gort.spectra(None, wk.DEFAULT_SOIL.reshape(4, 1), wl, user_leaf=0.5)
+    ang = np.array([[10.0], [0.0], [30.0], [20.0]])
+    rsurf = gort.brdf(st.reshape(6, 1), lut, ang, rl[0], tl[0], rs[0])
+    assert_close(rsurf[0, 0], np.array([0.050742404003082275, 0.056485203146758124, 0.063178656471069655,
+                                        0.067789806911394482]), "E2")
+    full = gort.lut(st.reshape(6, 1))
+    p = tmp_path / "lut.txt"
+    gort_b200.lut_write_text(full[0], str(p))
+    back = gort_b200.lut_read_text(str(p))
+    assert back[90] == 0.0 and back[91 + 90] == 0.0
+    keep = np.r_[0:90, 91:181, 182, 183]
+    assert_close(back[keep], full[0][keep], "LUT text round trip", rtol=1e-15)
+    r1 = gort.brdf(st.reshape(6, 1), back.reshape(1, -1), ang, rl[0], tl[0], rs[0])
+    r_o, _, _ = oracle.brdf(st, back, ang.T, rl[0], tl[0], rs[0])
+    assert_close(r1[0], r_o, "-P LUT")
+
+
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("nw", [5, 70, 300])
+def test_energy_random(gort, oracle, nw):
+    rng = np.random.Generator(np.random.PCG64(14 + nw))
+    M = 3
+    st = wk.random_structures(rng, M)
+    leaf = wk.random_leaves(rng, M)
+    wl = np.sort(rng.uniform(400, 2500, nw))
+    ang = np.array([[0.0, 10.0, 0.0, 0.0], [0.0, 0.0, 0.0, 0.0], [0.0, 30.0, 60.0, 75.0], [0.0, 40.0, 180.0, 300.0]])
+    lut = np.stack([oracle.lut(st[:, m]) for m in range(M)])
+    sp = [oracle.spectra(leaf[:, m], wk.DEFAULT_SOIL, wl) for m in range(M)]
+    rl = np.stack([s[0] for s in sp]); tl = np.stack([s[1] for s in sp]); rs = np.stack([s[2] for s in sp])
+    alb, fv, fs = gort.energy(st, lut, ang, rl, tl, rs)
+    for m in range(M):
+        a_o, v_o, s_o = oracle.energy(st[:, m], lut[m], ang.T, rl[m], tl[m], rs[m])
+        assert_close(alb[m], a_o, "albedo set %d" % m)
+        assert_close(fv[m], v_o, "favegt set %d" % m, rtol=1e-8)   # 1 - albedo - Fd2 + Fu2: cancellation, see DESIGN.md
+        assert_close(fs[m], s_o, "fasoil set %d" % m)
+
+
+def test_gauleg_nodes(gort, oracle):
+    x, w = gort.gauleg()
+    xo, wo = oracle.gauleg(32)
+    assert_close(x, xo, "abscissa", rtol=1e-14); assert_close(w, wo, "weights", rtol=1e-13)
+
+
+# ---------------------------------------------------------------------------------------------
+def test_c2_full_size_properties(gort, oracle):
+    """BASELINE config 2 at full size (11 664 lines x 2101 bands): oracle on a line subsample +
+    size-independent properties (azimuth mirror symmetry, K proportions sum, device == host API)."""
+    import torch
+    w = wk.c2_hemisphere()
+    st, ang, wl = w["structure"], w["angles"], w["wavelength"]
+    lut = gort.lut(st)
+    rl, tl, rs = gort.spectra(w["leaf"], w["soil"], wl)
+    rsurf, kprop = gort.brdf(st, lut, ang, rl[0], tl[0], rs[0], want_kprop=True)
+    assert rsurf.shape == (1, 11664, 2101)
+    assert np.isfinite(rsurf).all()
+    # oracle on every 97th line
+    idx = np.arange(0, ang.shape[1], 97)
+    lut_o = oracle.lut(st[:, 0])
+    sp_o = oracle.spectra(w["leaf"][:, 0], w["soil"][:, 0], wl)
+    r_o, _, k_o = oracle.brdf(st[:, 0], lut_o, ang[:, idx].T, *sp_o)
+    e = assert_close(rsurf[0, idx], r_o, "C2 subsample")
+    print("C2 subsample worst rel err %.3e" % e)
+    # mirror symmetry in relative azimuth: raz and 360 - raz give the same reflectance
+    R = rsurf[0].reshape(18, 18, 36, 2101)
+    for a in (1, 7, 17):
+        assert_close(R[:, :, a], R[:, :, 36 - a], "azimuth mirror %d" % a, rtol=1e-12)
+    # Kc + Kg + Kt + Kz == 1 wherever Kt was not clamped at 0
+    ks = kprop[0].sum(axis=1)
+    free = kprop[0][:, 2] > 0
+    assert np.max(np.abs(ks[free] - 1.0)) < 1e-12
+    # device-pointer API gives the same bits as the host-pointer API
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    out = torch.empty((1, 11664, 2101), dtype=torch.float64, device=dev)
+    gort.brdf_dev(t(st), t(lut), t(ang), t(rl[0]), t(tl[0]), t(rs[0]), out)
+    gort.synchronize()
+    assert np.array_equal(out.cpu().numpy(), rsurf)
