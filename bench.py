@@ -234,7 +234,8 @@ def main():
 
     T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
     d_st, d_lut, d_ang, d_rl, d_tl, d_rs = T(st), T(lut), T(ang), T(rl), T(tl), T(rs)
-    d_out = torch.empty((1, G, W), dtype=torch.float64, device=dev)
+    pitch = ((W + 15) // 16) * 16          # device rows padded to 128 B: every warp store is sector-aligned
+    d_out = torch.empty((1, G, pitch), dtype=torch.float64, device=dev)
     # the launching stream: a torch stream whose handle is passed through the C ABI, so that the
     # torch CUDA events below are recorded on the very stream the kernels run on
     ts = torch.cuda.Stream(device=dev)
@@ -304,6 +305,7 @@ def main():
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "c2", "lines": G, "wavelengths": W, "sets_per_gpu": 1,
                        "evals_per_gpu_per_step": evals_per_rank,
+                       "device_row_pitch_doubles": pitch,
                        "l2": "outputs are 196 MB per step (> 126 MB L2); no explicit flush",
                        "setup_not_timed": "gap-probability LUT + PROSPECT-D/Price spectra, computed once on the GPU"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d),

@@ -44,7 +44,8 @@ class _Options(C.Structure):
 
 class _Shape(C.Structure):
     _fields_ = [("n_sets", C.c_int), ("n_geom", C.c_int), ("n_wl", C.c_int),
-                ("geom_per_set", C.c_int), ("spectra_per_set", C.c_int), ("opt", _Options)]
+                ("geom_per_set", C.c_int), ("spectra_per_set", C.c_int), ("opt", _Options),
+                ("out_pitch", C.c_int)]
 
 
 _lib = None
@@ -209,8 +210,9 @@ class Gort:
 
     # ---- shapes ----
     @staticmethod
-    def _shape(n_sets, n_geom, n_wl, geom_per_set, spectra_per_set, beta=None, fd=None):
+    def _shape(n_sets, n_geom, n_wl, geom_per_set, spectra_per_set, beta=None, fd=None, out_pitch=0):
         sh = _Shape()
+        sh.out_pitch = int(out_pitch)
         sh.n_sets, sh.n_geom, sh.n_wl = n_sets, n_geom, n_wl
         sh.geom_per_set, sh.spectra_per_set = int(geom_per_set), int(spectra_per_set)
         sh.opt.use_beta = beta is not None
@@ -310,7 +312,9 @@ class Gort:
         gps = angles.dim() == 3
         sps = rleaf.dim() == 2
         G, W = angles.shape[-1], rleaf.shape[-1]
-        sh = self._shape(M, G, W, gps, sps, beta, fd)
+        # rsurf may be [M][G][pitch] with pitch >= W (a pitch that is a multiple of 4 keeps warp stores aligned)
+        pitch = rsurf.shape[-1]
+        sh = self._shape(M, G, W, gps, sps, beta, fd, out_pitch=pitch)
         self._check(self._lib.gort_brdf_batch_dev(self._h, stream, C.byref(sh), _ptr(structure), _ptr(lut),
                                                   _ptr(angles), _ptr(rleaf), _ptr(tleaf), _ptr(rsoil),
                                                   _ptr(rsurf), _ptr(scomp), _ptr(kprop)))

@@ -293,15 +293,20 @@ int gort_brdf_batch(gort_ctx *ctx, const gort_shape *shape, const double *struct
     TRYCUDA(ctx, cudaSetDevice(ctx->device), "cudaSetDevice");
     Staged d;
     TRY(stage_inputs(ctx, shape, structure, lut, angles, rleaf, tleaf, rsoil, &d));
-    size_t n = (size_t) shape->n_sets * shape->n_geom * shape->n_wl;
     size_t nl = (size_t) shape->n_sets * shape->n_geom;
+    // the device buffer uses the caller's row pitch so that the result comes back in ONE contiguous copy
+    // (a pitched 2-D copy costs more over PCIe than aligned rows save in the kernel); padding columns of a
+    // pitched host array are left undefined
+    const size_t W = shape->n_wl;
+    const size_t hp = shape->out_pitch > 0 ? (size_t) shape->out_pitch : W;
+    if (hp < W) return set_error(ctx, GORT_ERR_INVALID, "gort_brdf_batch: out_pitch smaller than n_wl");
     double *d_rsurf, *d_scomp, *d_kprop;
-    TRY(dout(ctx, 6, rsurf, n, &d_rsurf));
-    TRY(dout(ctx, 7, scomp, 4 * n, &d_scomp));
+    TRY(dout(ctx, 6, rsurf, nl * hp, &d_rsurf));
+    TRY(dout(ctx, 7, scomp, 4 * nl * hp, &d_scomp));
     TRY(dout(ctx, 8, kprop, 4 * nl, &d_kprop));
     TRY(launch_brdf(ctx, ctx->stream, *shape, d.st, d.lut, d.ang, d.rl, d.tl, d.rs, d_rsurf, d_scomp, d_kprop));
-    TRY(d2h(ctx, rsurf, d_rsurf, n));
-    TRY(d2h(ctx, scomp, d_scomp, 4 * n));
+    TRY(d2h(ctx, rsurf, d_rsurf, nl * hp));
+    TRY(d2h(ctx, scomp, d_scomp, 4 * nl * hp));
     TRY(d2h(ctx, kprop, d_kprop, 4 * nl));
     return check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "gort_brdf_batch");
 }

@@ -11,8 +11,10 @@
 //   rsurf_flat_kernel  W < 64 (band sets): one thread per (line, band).
 //   energy_kernel      one CTA per (set, sun line): 512 quadrature nodes' records in shared
 //                      memory, lanes = azimuth nodes, warp-shuffle reduction (gortt_albedo.c).
+#include <stdlib.h>
 #include "gort_device.cuh"
 #include "gort_internal.h"
+#include "gort_rsurf_wide.cuh"
 
 namespace gort {
 
@@ -32,11 +34,18 @@ geom_kernel(int n_sets, int n_geom, int geom_per_set, gort_options opt,
     Line g = line_from_degrees(angles[0 * na + a], angles[1 * na + a], angles[2 * na + a], angles[3 * na + a]);
     double fd = opt.use_fd ? opt.fd : cos(g.sza) / (cos(g.sza) + 0.09);       // gortt.c:290-291
     GeomRec r = geom_record(c, lut + (size_t) m * GORT_LUT_STRIDE, opt, g.vza, g.sza, g.raa, fd);
-    rec[0 * L + line] = r.Kc;  rec[1 * L + line] = r.Kg;  rec[2 * L + line] = r.Kt;
-    rec[3 * L + line] = r.Kz;  rec[4 * L + line] = r.Kpg; rec[5 * L + line] = r.Kpz;
-    rec[6 * L + line] = r.q;   rec[7 * L + line] = r.fd;  rec[8 * L + line] = r.mus;
-    rec[9 * L + line] = r.t0;  rec[10 * L + line] = r.tp0; rec[11 * L + line] = r.pe_s;
-    rec[12 * L + line] = r.pn0_s;
+    // packed 128-byte record: (Kc,Kg) (Kt,Kz) (K'g,K'z) (q,fd) | (mus,t0) (tp0,pe_s) (flags,pn0_s) (pad)
+    // flags bit0: the sun of this line differs from the previous line's (every sun-dependent term is a
+    // function of |sza| and the set only); bit1: first line of a parameter set
+    int flags = 0;
+    if (line % n_geom == 0) flags = 3;
+    else if (fabs(angles[2 * na + a]) != fabs(angles[2 * na + a - 1])) flags = 1;
+    double2* o = reinterpret_cast<double2*>(rec + (size_t) line * GORT_REC_STRIDE);
+    o[0] = make_double2(r.Kc, r.Kg);   o[1] = make_double2(r.Kt, r.Kz);
+    o[2] = make_double2(r.Kpg, r.Kpz); o[3] = make_double2(r.q, r.fd);
+    o[4] = make_double2(r.mus, r.t0);  o[5] = make_double2(r.tp0, r.pe_s);
+    o[6] = make_double2(__longlong_as_double((long long) flags), r.pn0_s);
+    o[7] = make_double2(0.0, 0.0);
     if (kprop) {
         kprop[4 * line + 0] = r.Kc; kprop[4 * line + 1] = r.Kg;
         kprop[4 * line + 2] = r.Kt; kprop[4 * line + 3] = r.Kz;
@@ -44,81 +53,8 @@ geom_kernel(int n_sets, int n_geom, int geom_per_set, gort_options opt,
 }
 
 // ------------------------------------------------------------------------------------------------
-template <int LPT>
 __global__ void __launch_bounds__(128)
-rsurf_wide_kernel(int n_sets, int n_geom, int n_wl, int spectra_per_set, int tile_lines,
-                  const double* __restrict__ structure, const double* __restrict__ lut,
-                  const double* __restrict__ rec,
-                  const double* __restrict__ rleaf, const double* __restrict__ tleaf,
-                  const double* __restrict__ rsoil,
-                  double* __restrict__ rsurf, double* __restrict__ scomp)
-{
-    extern __shared__ double srec[];     // [GORT_REC_FIELDS - 1][tile_lines]
-    const long L = (long) n_sets * n_geom;
-    const long line0 = (long) blockIdx.x * tile_lines;
-    const int nl = (int) min((long) tile_lines, L - line0);
-    for (int i = threadIdx.x; i < nl * 12; i += blockDim.x) {
-        int f = i / nl, l = i - f * nl;
-        srec[f * tile_lines + l] = rec[(size_t) f * L + line0 + l];
-    }
-    __syncthreads();
-
-    const int w0 = blockIdx.y * (blockDim.x * LPT) + threadIdx.x;
-    int wj[LPT];
-#pragma unroll
-    for (int j = 0; j < LPT; j++) wj[j] = w0 + j * blockDim.x;
-    if (wj[0] >= n_wl) return;
-
-    Canopy c;
-    LeafTerms Lf[LPT];
-    SunTerms S[LPT];
-    int cur_set = -1;
-    double p_fd = 0, p_mus = 0, p_t0 = 0, p_tp0 = 0, p_pe = 0;
-    for (int l = 0; l < nl; l++) {
-        const long line = line0 + l;
-        const int m = (int) (line / n_geom);
-        bool fresh = (m != cur_set);
-        if (fresh) {
-            cur_set = m;
-            c = canopy_load(structure, n_sets, m, lut);
-            const size_t sb = spectra_per_set ? (size_t) m * n_wl : 0;
-#pragma unroll
-            for (int j = 0; j < LPT; j++) {
-                int w = min(wj[j], n_wl - 1);
-                Lf[j] = leaf_terms(c, rleaf[sb + w], tleaf[sb + w], rsoil[sb + w]);
-            }
-        }
-        const double fd = srec[7 * tile_lines + l], mus = srec[8 * tile_lines + l];
-        const double t0 = srec[9 * tile_lines + l], tp0 = srec[10 * tile_lines + l];
-        const double pe = srec[11 * tile_lines + l];
-        if (fresh || fd != p_fd || mus != p_mus || t0 != p_t0 || tp0 != p_tp0 || pe != p_pe) {
-            p_fd = fd; p_mus = mus; p_t0 = t0; p_tp0 = tp0; p_pe = pe;
-#pragma unroll
-            for (int j = 0; j < LPT; j++) S[j] = sun_terms(c, Lf[j], fd, mus, t0, tp0, pe);
-        }
-        const double Kc = srec[0 * tile_lines + l], Kg = srec[1 * tile_lines + l];
-        const double Kt = srec[2 * tile_lines + l], Kz = srec[3 * tile_lines + l];
-        const double Kpg = srec[4 * tile_lines + l], Kpz = srec[5 * tile_lines + l];
-        const double q = srec[6 * tile_lines + l];
-#pragma unroll
-        for (int j = 0; j < LPT; j++) {
-            double C;
-            double r = view_rsurf(c, Lf[j], S[j], fd, q, Kc, Kg, Kt, Kz, Kpg, Kpz, C);
-            if (wj[j] < n_wl) {
-                size_t o = (size_t) line * n_wl + wj[j];
-                rsurf[o] = r;
-                if (scomp) {
-                    double4 v = make_double4(C, S[j].G, S[j].T, S[j].Z);
-                    *reinterpret_cast<double4*>(scomp + 4 * o) = v;
-                }
-            }
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
-rsurf_flat_kernel(int n_sets, int n_geom, int n_wl, int spectra_per_set,
+rsurf_flat_kernel(int n_sets, int n_geom, int n_wl, int spectra_per_set, long pitch,
                   const double* __restrict__ structure, const double* __restrict__ lut,
                   const double* __restrict__ rec,
                   const double* __restrict__ rleaf, const double* __restrict__ tleaf,
@@ -135,13 +71,49 @@ rsurf_flat_kernel(int n_sets, int n_geom, int n_wl, int spectra_per_set,
     Canopy c = canopy_load(structure, n_sets, m, lut);
     const size_t sb = (spectra_per_set ? (size_t) m * n_wl : 0) + w;
     LeafTerms Lf = leaf_terms(c, rleaf[sb], tleaf[sb], rsoil[sb]);
-    const double fd = rec[7 * L + line];
-    SunTerms S = sun_terms(c, Lf, fd, rec[8 * L + line], rec[9 * L + line], rec[10 * L + line], rec[11 * L + line]);
+    const double2* rr = reinterpret_cast<const double2*>(rec + (size_t) line * GORT_REC_STRIDE);
+    const double2 v0 = rr[0], v1 = rr[1], v2 = rr[2], v3 = rr[3], s0v = rr[4], s1v = rr[5];
+    const double fd = v3.y;
+    SunTerms S = sun_terms(c, Lf, fd, s0v.x, s0v.y, s1v.x, s1v.y);
     double C;
-    double r = view_rsurf(c, Lf, S, fd, rec[6 * L + line], rec[0 * L + line], rec[1 * L + line],
-                          rec[2 * L + line], rec[3 * L + line], rec[4 * L + line], rec[5 * L + line], C);
-    rsurf[e] = r;
-    if (scomp) *reinterpret_cast<double4*>(scomp + 4 * e) = make_double4(C, S.G, S.T, S.Z);
+    double r = view_rsurf(c, Lf, S, fd, v3.x, v0.x, v0.y, v1.x, v1.y, v2.x, v2.y, C);
+    const size_t o = (size_t) line * pitch + w;
+    rsurf[o] = r;
+    if (scomp) *reinterpret_cast<double4*>(scomp + 4 * o) = make_double4(C, S.G, S.T, S.Z);
+}
+
+template <int LPT, bool SCOMP, int MINB>
+static int launch_wide(gort_ctx *ctx, cudaStream_t s, const gort_shape &sh, long L, const double *structure,
+                       const double *lut, const double *rec, const double *rleaf, const double *tleaf,
+                       const double *rsoil, double *rsurf, double *scomp)
+{
+    // wavelength chunks: as few as possible with <= 256 threads per CTA, lanes spread evenly
+    const int n_chunks = (sh.n_wl + LPT * 256 - 1) / (LPT * 256);
+    int threads = (sh.n_wl + n_chunks * LPT - 1) / (n_chunks * LPT);
+    threads = ((threads + 31) / 32) * 32;
+    WideArgs a;
+    a.n_sets = sh.n_sets; a.n_geom = sh.n_geom; a.n_wl = sh.n_wl; a.spectra_per_set = sh.spectra_per_set;
+    a.chunk = LPT * threads;
+    a.pitch = sh.out_pitch > 0 ? sh.out_pitch : sh.n_wl;
+    a.structure = structure; a.lut = lut; a.rec = rec; a.rleaf = rleaf; a.tleaf = tleaf; a.rsoil = rsoil;
+    a.rsurf = rsurf; a.scomp = scomp;
+    const size_t smem = sizeof(double2) * 8 * WIDE_STAGE_LINES + sizeof(int) * WIDE_STAGE_LINES
+                      + sizeof(double) * WIDE_NLEAF * (size_t) a.chunk;
+    auto kern = rsurf_wide_kernel<LPT, SCOMP, MINB>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    if (e != cudaSuccess) return check_cuda(ctx, e, "rsurf_wide_kernel shared memory");
+    int occ = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem);
+    if (e != cudaSuccess || occ < 1) occ = 1;
+    // one resident wave: grid.y contiguous line ranges so that n_chunks * grid.y ~ SMs * occupancy
+    long nby = ((long) ctx->sm_count * occ) / n_chunks;
+    if (nby < 1) nby = 1;
+    if (nby > L) nby = L;
+    a.lines_per_cta = (L + nby - 1) / nby;
+    nby = (L + a.lines_per_cta - 1) / a.lines_per_cta;
+    dim3 grid((unsigned) n_chunks, (unsigned) nby);
+    kern<<<grid, threads, smem, s>>>(a);
+    return GORT_OK;
 }
 
 int launch_brdf(gort_ctx *ctx, cudaStream_t s, const gort_shape &sh, const double *structure,
@@ -151,7 +123,9 @@ int launch_brdf(gort_ctx *ctx, cudaStream_t s, const gort_shape &sh, const doubl
     if (sh.n_sets <= 0 || sh.n_geom <= 0 || sh.n_wl <= 0)
         return set_error(ctx, GORT_ERR_INVALID, "gort_brdf: n_sets, n_geom and n_wl must be positive");
     const long L = (long) sh.n_sets * sh.n_geom;
-    double *rec = (double *) workspace(ctx, sizeof(double) * GORT_REC_FIELDS * (size_t) L);
+    const long pitch = sh.out_pitch > 0 ? sh.out_pitch : sh.n_wl;
+    if (pitch < sh.n_wl) return set_error(ctx, GORT_ERR_INVALID, "gort_brdf: out_pitch smaller than n_wl");
+    double *rec = (double *) workspace(ctx, sizeof(double) * GORT_REC_STRIDE * (size_t) L);
     if (!rec) return GORT_ERR_NOMEM;
     cudaEvent_t *ev = (ctx->prof_ev && ctx->prof_n < ctx->prof_cap) ? ctx->prof_ev + 3 * ctx->prof_n : NULL;
     if (ev) cudaEventRecord(ev[0], s);
@@ -164,18 +138,23 @@ int launch_brdf(gort_ctx *ctx, cudaStream_t s, const gort_shape &sh, const doubl
     }
     if (ev) cudaEventRecord(ev[1], s);
     if (sh.n_wl >= 64) {
-        const int threads = 128;
-        const int LPT = 2;
-        int tile = 32;
-        dim3 grid((unsigned) ((L + tile - 1) / tile), (unsigned) ((sh.n_wl + threads * LPT - 1) / (threads * LPT)));
-        size_t smem = sizeof(double) * 12 * tile;
-        rsurf_wide_kernel<LPT><<<grid, threads, smem, s>>>(sh.n_sets, sh.n_geom, sh.n_wl, sh.spectra_per_set, tile,
-                                                           structure, lut, rec, rleaf, tleaf, rsoil, rsurf, scomp);
+        // tuning knobs (development only): GORT_WIDE_LPT in {2,4}, GORT_WIDE_MINB in {2,3,4}
+        static int lpt = getenv("GORT_WIDE_LPT") ? atoi(getenv("GORT_WIDE_LPT")) : 4;
+        static int minb = getenv("GORT_WIDE_MINB") ? atoi(getenv("GORT_WIDE_MINB")) : 2;
+        int rc;
+#define WIDE_ARGS ctx, s, sh, L, structure, lut, rec, rleaf, tleaf, rsoil, rsurf, scomp
+        if (scomp) rc = launch_wide<2, true, 3>(WIDE_ARGS);
+        else if (lpt == 4) rc = (minb <= 2) ? launch_wide<4, false, 2>(WIDE_ARGS) : launch_wide<4, false, 3>(WIDE_ARGS);
+        else if (minb <= 2) rc = launch_wide<2, false, 2>(WIDE_ARGS);
+        else if (minb == 3) rc = launch_wide<2, false, 3>(WIDE_ARGS);
+        else rc = launch_wide<2, false, 4>(WIDE_ARGS);
+#undef WIDE_ARGS
+        if (rc != GORT_OK) return rc;
     } else {
         const int threads = 128;
         long total = L * sh.n_wl;
         long blocks = (total + threads - 1) / threads;
-        rsurf_flat_kernel<<<(unsigned) blocks, threads, 0, s>>>(sh.n_sets, sh.n_geom, sh.n_wl, sh.spectra_per_set,
+        rsurf_flat_kernel<<<(unsigned) blocks, threads, 0, s>>>(sh.n_sets, sh.n_geom, sh.n_wl, sh.spectra_per_set, pitch,
                                                                 structure, lut, rec, rleaf, tleaf, rsoil, rsurf, scomp);
     }
     ctx->launches++;

@@ -92,6 +92,7 @@ struct GeomRec {
     double pn0_s;                       // p_neq0_heq0_sza (energy balance, gortt_albedo.c:37)
 };
 #define GORT_REC_FIELDS 13
+#define GORT_REC_STRIDE 16      // doubles per packed line record in HBM (128 bytes)
 
 // gortt.c:872-915 for one zenith angle.  The reference indexes p_n0[0][ceil(pos)] with no bound;
 // for zenith = 90 deg rounding can give 91 (one past the table): clamp to the last row.

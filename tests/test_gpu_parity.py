@@ -292,3 +292,9 @@ def test_c2_full_size_properties(gort, oracle):
     gort.brdf_dev(t(st), t(lut), t(ang), t(rl[0]), t(tl[0]), t(rs[0]), out)
     gort.synchronize()
     assert np.array_equal(out.cpu().numpy(), rsurf)
+    # padded row pitch (aligned warp stores): same bits in the first W columns, padding untouched
+    outp = torch.full((1, 11664, 2112), -7.0, dtype=torch.float64, device=dev)
+    gort.brdf_dev(t(st), t(lut), t(ang), t(rl[0]), t(tl[0]), t(rs[0]), outp)
+    gort.synchronize()
+    hp = outp.cpu().numpy()
+    assert np.array_equal(hp[:, :, :2101], rsurf) and np.all(hp[:, :, 2101:] == -7.0)
