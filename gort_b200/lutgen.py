@@ -1,0 +1,69 @@
+"""LUT generation over a structural-parameter grid on 1-8 GPUs (BASELINE.json config 5).
+
+    python -m gort_b200.lutgen --grid 8,8,4,8,8,8 --out luts/            # one GPU
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 \
+        -m gort_b200.lutgen --grid 8,8,4,8,8,8 --out luts/                # eight GPUs
+
+Each rank computes the KOpen / P(n) LUTs of its block of parameter sets with the CUDA kernel
+(gort_lut_batch_dev), one NCCL all-gather assembles them on every rank, and rank 0 writes them in the
+reference's "-W" text layout so that `gortt -P luts/lut_000123.txt ...` can consume them.
+"""
+import argparse
+import json
+import time
+
+import numpy as np
+import torch
+
+from . import workloads as wk
+from .api import Gort, LUT_FULL, LUT_Q08, LUT_STRIDE
+from .parallel import init_distributed, lut_generate_sharded, write_lut_directory
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--grid", default="8,8,4,8,8,8", help="points along r, b/r, h1, h2-h1, cover, favd")
+    ap.add_argument("--out", default=None, help="directory for the -W layout text files (rank 0)")
+    ap.add_argument("--limit", type=int, default=0, help="only the first N grid points")
+    ap.add_argument("--q08", action="store_true")
+    ap.add_argument("--write-max", type=int, default=4096, help="cap on the number of text files written")
+    args = ap.parse_args()
+
+    rank, local_rank, world = init_distributed()
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    g = Gort(local_rank)
+    st = wk.c5_lut_grid(tuple(int(x) for x in args.grid.split(",")))["structure"]
+    if args.limit:
+        st = np.ascontiguousarray(st[:, :args.limit])
+    M = st.shape[1]
+    stream = torch.cuda.current_stream()
+
+    def compute_local(block):
+        d_st = torch.from_numpy(block).to(dev)
+        out = torch.empty((block.shape[1], LUT_STRIDE), dtype=torch.float64, device=dev)
+        ts = torch.cuda.Stream(device=dev)
+        ts.wait_stream(stream)
+        g.lut_dev(d_st, out, LUT_Q08 if args.q08 else LUT_FULL, stream=ts.cuda_stream)
+        stream.wait_stream(ts)
+        return out
+
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    luts = lut_generate_sharded(st, compute_local, rank, world)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    if rank == 0:
+        n_written = 0
+        if args.out:
+            n_written = write_lut_directory(luts[:args.write_max], args.out)
+        print(json.dumps({"luts": M, "gpus": world, "seconds": dt, "luts_per_s": M / dt,
+                          "allgather_bytes": M * LUT_STRIDE * 8, "files_written": n_written,
+                          "nan_luts": int(torch.isnan(luts).any(dim=1).sum())}))
+    g.close()
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,96 @@
+"""Multi-GPU plumbing: one process per GPU, torch.distributed (NCCL over NVLink on GPUs, gloo on CPU for
+the host-logic tests).
+
+The GORT path shards embarrassingly: every (parameter set, input line) unit is
+independent, so ranks own contiguous blocks of parameter sets (or of lines) and never exchange data on
+the compute path.  The ONE collective is the all-gather that assembles gap-probability LUTs on every
+rank (BASELINE.json config 5), after which rank 0 writes the reference's "-W" text layout.
+
+Nothing here does model arithmetic: `compute_local` is the GPU call (Gort.lut_dev) in production and
+the oracle in the CPU tests.
+"""
+import os
+from pathlib import Path
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from .api import LUT_STRIDE, lut_write_text
+
+
+def shard_range(n, rank, world):
+    """Contiguous block [lo, hi) of n units owned by `rank`: sizes differ by at most one, larger blocks first."""
+    base, extra = divmod(n, world)
+    lo = rank * base + min(rank, extra)
+    hi = lo + base + (1 if rank < extra else 0)
+    return lo, hi
+
+
+def shard_counts(n, world):
+    return [shard_range(n, r, world)[1] - shard_range(n, r, world)[0] for r in range(world)]
+
+
+def init_distributed(backend=None):
+    """Read RANK / LOCAL_RANK / WORLD_SIZE / MASTER_* (torchrun); returns (rank, local_rank, world)."""
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29512")
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local_rank)
+            dist.init_process_group(backend, device_id=torch.device("cuda", local_rank))
+        else:
+            dist.init_process_group(backend)
+    return rank, local_rank, world
+
+
+def allgather_rows(local, n_total, rank, world):
+    """All-gather row blocks of a [n_local, K] tensor into [n_total, K] on every rank.
+
+    Blocks follow shard_range(); ranks with one row fewer pad to the common block size so that a single
+    all_gather_into_tensor (one NCCL all-gather over NVLink / NVSwitch) moves everything."""
+    if world == 1:
+        assert local.shape[0] == n_total
+        return local
+    counts = shard_counts(n_total, world)
+    assert local.shape[0] == counts[rank], (local.shape, counts, rank)
+    cmax = max(counts)
+    K = local.shape[1]
+    if local.shape[0] < cmax:
+        pad = torch.zeros((cmax - local.shape[0], K), dtype=local.dtype, device=local.device)
+        local = torch.cat([local, pad], dim=0)
+    out = torch.empty((world * cmax, K), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, local.contiguous())
+    if all(c == cmax for c in counts):
+        return out
+    keep = torch.cat([torch.arange(r * cmax, r * cmax + counts[r], device=local.device) for r in range(world)])
+    return out.index_select(0, keep)
+
+
+def lut_generate_sharded(structure, compute_local, rank, world, device=None):
+    """LUTs for all M parameter sets of `structure` ([6][M] numpy), sharded by parameter set.
+
+    compute_local(structure_block [6][m]) -> [m][184] tensor on `device`.
+    Returns the assembled [M][184] tensor, identical on every rank."""
+    M = structure.shape[1]
+    lo, hi = shard_range(M, rank, world)
+    block = np.ascontiguousarray(structure[:, lo:hi])
+    local = compute_local(block)
+    assert local.shape == (hi - lo, LUT_STRIDE)
+    return allgather_rows(local, M, rank, world)
+
+
+def write_lut_directory(luts, out_dir, names=None):
+    """Rank 0: one "-W"-layout text file per parameter set (gortt.c:123-128), readable by `gortt -P`."""
+    out_dir = Path(out_dir)
+    out_dir.mkdir(parents=True, exist_ok=True)
+    luts = luts.detach().cpu().numpy() if isinstance(luts, torch.Tensor) else np.asarray(luts)
+    for k in range(luts.shape[0]):
+        name = names[k] if names is not None else "lut_%06d.txt" % k
+        lut_write_text(luts[k], str(out_dir / name))
+    return luts.shape[0]
