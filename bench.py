@@ -254,7 +254,6 @@ def main():
         sampler.start()
         time.sleep(0.25)
     l0 = g.launch_count()
-    g.profile_begin(args.steps)
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record(ts)
@@ -263,8 +262,15 @@ def main():
     e1.record(ts)
     barrier()
     ms_total = e0.elapsed_time(e1)
-    geom_ms, rsurf_ms, nprof = g.profile_end()
     launches = g.launch_count() - l0
+    # per-kernel durations: the same K steps again, this time with CUDA events recorded on the launching
+    # stream around each kernel (gort_profile_begin/end).  Kept out of the timed region above because an
+    # event between the two launches of a step would defeat their programmatic-dependent-launch overlap.
+    g.profile_begin(args.steps)
+    for _ in range(args.steps):
+        step_dev()
+    barrier()
+    geom_ms, rsurf_ms, nprof = g.profile_end()
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- end-to-end through the host-pointer C ABI (pinned host buffers, copies inside) ----

@@ -19,33 +19,83 @@
 namespace gort {
 
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
+// geom_kernel: one CTA = 32 lines x 5 role warps.  A line's record is ~4200 dependent SASS instructions
+// when one thread computes it (45 FP64 libm calls); with a few hundred warps on 592 SM sub-partitions the
+// kernel is pure latency (18.6 us for 11 664 lines, ncu profiles/r1d).  The roles below have no data
+// dependence on each other, so five warps compute them side by side and warp 0 combines them:
+//   warp 0  pass at the actual relative azimuth (overlap, Kg, f, F)       gortt_brdf.c:7-100, :171-238
+//   warp 1  pass at raa = 0                                              gortt_brdf.c:143-146
+//   warp 2  pass at raa = pi                                             gortt_brdf.c:147-150
+//   warp 3  exp terms of Kz / K'g / t0 and the mutual-shadowing beta     gortt.c:439-449, gortt_brdf.c:223-232
+//   warp 4  zenith interpolation of the LUT and the Kuusk hotspot        gortt.c:872-915, gortt_brdf.c:638-702
+#define GEOM_ROLES 5
+__global__ void __launch_bounds__(32 * GEOM_ROLES)
 geom_kernel(int n_sets, int n_geom, int geom_per_set, gort_options opt,
             const double* __restrict__ structure, const double* __restrict__ lut,
             const double* __restrict__ angles, double* __restrict__ rec, double* __restrict__ kprop)
 {
+    // let the dependent per-wavelength kernel start its prologue (leaf terms) while this grid runs; it still
+    // waits for this grid's completion (griddepcontrol.wait) before it reads a record
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    __shared__ double ex[12][32];
     const long L = (long) n_sets * n_geom;
-    long line = (long) blockIdx.x * blockDim.x + threadIdx.x;
-    if (line >= L) return;
-    int m = (int) (line / n_geom);
-    long a = geom_per_set ? line : (line - (long) m * n_geom);
-    long na = geom_per_set ? L : n_geom;
-    Canopy c = canopy_load(structure, n_sets, m, lut);
-    Line g = line_from_degrees(angles[0 * na + a], angles[1 * na + a], angles[2 * na + a], angles[3 * na + a]);
-    double fd = opt.use_fd ? opt.fd : cos(g.sza) / (cos(g.sza) + 0.09);       // gortt.c:290-291
-    GeomRec r = geom_record(c, lut + (size_t) m * GORT_LUT_STRIDE, opt, g.vza, g.sza, g.raa, fd);
-    // packed 128-byte record: (Kc,Kg) (Kt,Kz) (K'g,K'z) (q,fd) | (mus,t0) (tp0,pe_s) (flags,pn0_s) (pad)
+    const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
+    const long line_raw = (long) blockIdx.x * 32 + lane;
+    const long line = min(line_raw, L - 1);
+    const int m = (int) (line / n_geom);
+    const long a = geom_per_set ? line : (line - (long) m * n_geom);
+    const long na = geom_per_set ? L : n_geom;
+    const Canopy c = canopy_load(structure, n_sets, m, lut);
+    const Line g = line_from_degrees(angles[0 * na + a], angles[1 * na + a], angles[2 * na + a], angles[3 * na + a]);
+    // roles 0-2 run ONE copy of the pass code with their own relative azimuth (three inlined copies of the
+    // libm-heavy pass made the kernel instruction-fetch bound: stall_no_instruction was its top stall).
+    // The raa-independent crown terms (2 exp, acos) come from role 3 through shared memory: named barrier 1
+    // joins warps 0-3 half-way, so those terms leave the critical path of the passes.
+    Primed P;
+    Pass pa = {0.0, 0.0, 0.0};
+    if (role < 4) P = primed_trig(c, g.vza, g.sza);
+    if (role < 3) {
+        double raa = g.raa, cr = 1.0, sr = 0.0;
+        if (role == 0) sincos(g.raa, &sr, &cr);
+        else if (role == 1) raa = 0.0;
+        else { raa = GORT_PI; cr = -1.0; sr = GORT_SIN_PI; }
+        const PassA a1 = kc_pass_a(c, P, cr, sr);
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        CrownLite s;
+        s.Mv = ex[9][lane]; s.theta_Mi = ex[10][lane]; s.Gamma_v = ex[11][lane];
+        const bool vgs = fabs(g.vza) > fabs(g.sza);
+        pa = kc_pass_b(P, a1, s, vgs, raa, cr);
+        if (role > 0) ex[role - 1][lane] = pa.f * pa.F;
+    } else if (role == 3) {
+        const CrownLite s = crown_lite(c, P.t);
+        ex[9][lane] = s.Mv; ex[10][lane] = s.theta_Mi; ex[11][lane] = s.Gamma_v;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const Tail tl = tail_terms(c, P, opt);
+        ex[2][lane] = tl.e_v; ex[3][lane] = tl.e_s; ex[4][lane] = tl.t0; ex[5][lane] = tl.beta;
+    } else {
+        double sr, cr;
+        sincos(g.raa, &sr, &cr);
+        const Hot h = hotspot(c, lut + (size_t) m * GORT_LUT_STRIDE, g.vza, g.sza, cr);
+        ex[6][lane] = h.kuusk; ex[7][lane] = h.pn0_s; ex[8][lane] = h.pe_s;
+    }
+    __syncthreads();
+    if (role != 0 || line_raw >= L) return;
+    Tail tl; Hot h;
+    tl.e_v = ex[2][lane]; tl.e_s = ex[3][lane]; tl.t0 = ex[4][lane]; tl.beta = ex[5][lane];
+    h.kuusk = ex[6][lane]; h.pn0_s = ex[7][lane]; h.pe_s = ex[8][lane];
+    const double fd = opt.use_fd ? opt.fd : cos(g.sza) / (cos(g.sza) + 0.09);       // gortt.c:290-291
+    const GeomRec r = geom_combine(c, P, pa, ex[0][lane], ex[1][lane], tl, h, g.raa, fd);
     // flags bit0: the sun of this line differs from the previous line's (every sun-dependent term is a
     // function of |sza| and the set only); bit1: first line of a parameter set
     int flags = 0;
     if (line % n_geom == 0) flags = 3;
     else if (fabs(angles[2 * na + a]) != fabs(angles[2 * na + a - 1])) flags = 1;
     double2* o = reinterpret_cast<double2*>(rec + (size_t) line * GORT_REC_STRIDE);
-    o[0] = make_double2(r.Kc, r.Kg);   o[1] = make_double2(r.Kt, r.Kz);
-    o[2] = make_double2(r.Kpg, r.Kpz); o[3] = make_double2(r.q, r.fd);
+    o[0] = make_double2(r.cA, r.Kc);   o[1] = make_double2(r.cG, r.cZ);
+    o[2] = make_double2(r.Kt, __longlong_as_double((long long) flags));
+    o[3] = make_double2(r.q, r.fd);
     o[4] = make_double2(r.mus, r.t0);  o[5] = make_double2(r.tp0, r.pe_s);
-    o[6] = make_double2(__longlong_as_double((long long) flags), r.pn0_s);
-    o[7] = make_double2(0.0, 0.0);
+    o[6] = make_double2(r.Kpg, r.Kpz); o[7] = make_double2(r.Kg, r.Kz);
     if (kprop) {
         kprop[4 * line + 0] = r.Kc; kprop[4 * line + 1] = r.Kg;
         kprop[4 * line + 2] = r.Kt; kprop[4 * line + 3] = r.Kz;
@@ -72,11 +122,12 @@ rsurf_flat_kernel(int n_sets, int n_geom, int n_wl, int spectra_per_set, long pi
     const size_t sb = (spectra_per_set ? (size_t) m * n_wl : 0) + w;
     LeafTerms Lf = leaf_terms(c, rleaf[sb], tleaf[sb], rsoil[sb]);
     const double2* rr = reinterpret_cast<const double2*>(rec + (size_t) line * GORT_REC_STRIDE);
-    const double2 v0 = rr[0], v1 = rr[1], v2 = rr[2], v3 = rr[3], s0v = rr[4], s1v = rr[5];
+    // (cA,Kc) (cG,cZ) (Kt,flags) (q,fd) | (mus,t0) (tp0,pe_s) (K'g,K'z) (Kg,Kz)
+    const double2 v0 = rr[0], v2 = rr[2], v3 = rr[3], s0v = rr[4], s1v = rr[5], v6 = rr[6], v7 = rr[7];
     const double fd = v3.y;
     SunTerms S = sun_terms(c, Lf, fd, s0v.x, s0v.y, s1v.x, s1v.y);
     double C;
-    double r = view_rsurf(c, Lf, S, fd, v3.x, v0.x, v0.y, v1.x, v1.y, v2.x, v2.y, C);
+    double r = view_rsurf(c, Lf, S, fd, v3.x, v0.y, v7.x, v2.x, v7.y, v6.x, v6.y, C);
     const size_t o = (size_t) line * pitch + w;
     rsurf[o] = r;
     if (scomp) *reinterpret_cast<double4*>(scomp + 4 * o) = make_double4(C, S.G, S.T, S.Z);
@@ -85,7 +136,7 @@ rsurf_flat_kernel(int n_sets, int n_geom, int n_wl, int spectra_per_set, long pi
 template <int LPT, bool SCOMP, int MINB>
 static int launch_wide(gort_ctx *ctx, cudaStream_t s, const gort_shape &sh, long L, const double *structure,
                        const double *lut, const double *rec, const double *rleaf, const double *tleaf,
-                       const double *rsoil, double *rsurf, double *scomp)
+                       const double *rsoil, double *rsurf, double *scomp, bool pdl)
 {
     // wavelength chunks: as few as possible with <= 256 threads per CTA, lanes spread evenly
     const int n_chunks = (sh.n_wl + LPT * 256 - 1) / (LPT * 256);
@@ -94,10 +145,11 @@ static int launch_wide(gort_ctx *ctx, cudaStream_t s, const gort_shape &sh, long
     WideArgs a;
     a.n_sets = sh.n_sets; a.n_geom = sh.n_geom; a.n_wl = sh.n_wl; a.spectra_per_set = sh.spectra_per_set;
     a.chunk = LPT * threads;
+    a.pdl = pdl ? 1 : 0;
     a.pitch = sh.out_pitch > 0 ? sh.out_pitch : sh.n_wl;
     a.structure = structure; a.lut = lut; a.rec = rec; a.rleaf = rleaf; a.tleaf = tleaf; a.rsoil = rsoil;
     a.rsurf = rsurf; a.scomp = scomp;
-    const size_t smem = sizeof(double2) * 8 * WIDE_STAGE_LINES + sizeof(int) * WIDE_STAGE_LINES
+    const size_t smem = sizeof(double2) * 8 * WIDE_STAGE_LINES + sizeof(unsigned) * (WIDE_STAGE_LINES / 32)
                       + sizeof(double) * WIDE_NLEAF * (size_t) a.chunk;
     auto kern = rsurf_wide_kernel<LPT, SCOMP, MINB>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
@@ -111,9 +163,18 @@ static int launch_wide(gort_ctx *ctx, cudaStream_t s, const gort_shape &sh, long
     if (nby > L) nby = L;
     a.lines_per_cta = (L + nby - 1) / nby;
     nby = (L + a.lines_per_cta - 1) / a.lines_per_cta;
-    dim3 grid((unsigned) n_chunks, (unsigned) nby);
-    kern<<<grid, threads, smem, s>>>(a);
-    return GORT_OK;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned) n_chunks, (unsigned) nby);
+    cfg.blockDim = dim3((unsigned) threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    e = cudaLaunchKernelEx(&cfg, kern, a);
+    return check_cuda(ctx, e, "rsurf_wide_kernel launch");
 }
 
 int launch_brdf(gort_ctx *ctx, cudaStream_t s, const gort_shape &sh, const double *structure,
@@ -130,8 +191,8 @@ int launch_brdf(gort_ctx *ctx, cudaStream_t s, const gort_shape &sh, const doubl
     cudaEvent_t *ev = (ctx->prof_ev && ctx->prof_n < ctx->prof_cap) ? ctx->prof_ev + 3 * ctx->prof_n : NULL;
     if (ev) cudaEventRecord(ev[0], s);
     {
-        int threads = 128;
-        long blocks = (L + threads - 1) / threads;
+        int threads = 32 * GEOM_ROLES;
+        long blocks = (L + 31) / 32;
         geom_kernel<<<(unsigned) blocks, threads, 0, s>>>(sh.n_sets, sh.n_geom, sh.geom_per_set, sh.opt,
                                                           structure, lut, angles, rec, kprop);
         ctx->launches++;
@@ -141,9 +202,13 @@ int launch_brdf(gort_ctx *ctx, cudaStream_t s, const gort_shape &sh, const doubl
         // tuning knobs (development only): GORT_WIDE_LPT in {2,4}, GORT_WIDE_MINB in {2,3,4}
         static int lpt = getenv("GORT_WIDE_LPT") ? atoi(getenv("GORT_WIDE_LPT")) : 4;
         static int minb = getenv("GORT_WIDE_MINB") ? atoi(getenv("GORT_WIDE_MINB")) : 2;
+        static int use_pdl = getenv("GORT_NO_PDL") ? 0 : 1;
+        // programmatic dependent launch: the kernel's (set, lambda) prologue overlaps geom_kernel.  Off while
+        // per-kernel events are being recorded (an event between the two launches would time the overlap)
+        const bool pdl = use_pdl && !ev;
         int rc;
-#define WIDE_ARGS ctx, s, sh, L, structure, lut, rec, rleaf, tleaf, rsoil, rsurf, scomp
-        if (scomp) rc = launch_wide<2, true, 3>(WIDE_ARGS);
+#define WIDE_ARGS ctx, s, sh, L, structure, lut, rec, rleaf, tleaf, rsoil, rsurf, scomp, pdl
+        if (scomp) rc = launch_wide<2, true, 2>(WIDE_ARGS);
         else if (lpt == 4) rc = (minb <= 2) ? launch_wide<4, false, 2>(WIDE_ARGS) : launch_wide<4, false, 3>(WIDE_ARGS);
         else if (minb <= 2) rc = launch_wide<2, false, 2>(WIDE_ARGS);
         else if (minb == 3) rc = launch_wide<2, false, 3>(WIDE_ARGS);

@@ -2,17 +2,23 @@
 // (W >= 64), the dominant kernel of the BRDF path.
 //
 // Work decomposition (grid.x = wavelength chunks, grid.y = contiguous line ranges):
-//   * a CTA owns one wavelength chunk (LPT wavelengths per thread, lanes = consecutive wavelengths,
-//     so every warp store is a contiguous 256-byte run of one output row) and walks a CONTIGUOUS
-//     range of input lines, sized so that the whole grid is one resident wave;
+//   * a CTA owns one wavelength chunk and walks a CONTIGUOUS range of input lines, sized so that the
+//     whole grid is one resident wave.  Warp w of the CTA owns the 32*LPT consecutive wavelengths
+//     [w*32*LPT, (w+1)*32*LPT) of the chunk; its j-th store of a line lands 256*j bytes after the first,
+//     so the LPT stores of a line share one address register and use immediate offsets;
 //   * the packed 128-byte line records written by geom_kernel are staged into shared memory
-//     WIDE_STAGE_LINES at a time (a straight coalesced copy) and cut into "runs" of lines that share
-//     parameter set and sun (flags computed by geom_kernel from the input angles);
+//     WIDE_STAGE_LINES at a time and cut into "runs" of lines that share parameter set and sun
+//     (flags computed by geom_kernel from the input angles);
 //   * the (set, lambda) terms (exp, sqrt, four divides) are computed once per set into shared memory;
 //   * the (sun, lambda) terms are re-derived only at the start of a run and then live in registers:
-//     A, PD, FCf, G, Z, T;
-//   * inside a run only the view-dependent part remains per (line, lambda): 4 broadcast LDS.128 per
-//     line, 9 FP64 instructions and one coalesced 8-byte store per evaluation, no branches.
+//     A, PDF, G, Z, T;
+//   * inside a run only the view-dependent part remains per (line, lambda).  gortt.c:557,
+//         rsurf = Kc*C + Kg*G + Kt*T + Kz*Z,   C = fd*(A*q + PD + ke*(G*K'g + Z*K'z)) + FCf,
+//     is regrouped by per-(sun, lambda) term,
+//         rsurf = cA*A + Kc*PDF + cG*G + cZ*Z + Kt*T,
+//     with the five per-line coefficients prepared by geom_kernel: 3 broadcast LDS.128 per line, then
+//     5 FP64 instructions and one coalesced 8-byte store per evaluation, no branches.
+//     (With scomp requested the crown signature C itself is an output and the long form is used.)
 // HBM traffic is 8 B per evaluation (rsurf) -- the binding roofline for this kernel.
 // Output rows are `pitch` doubles apart; a pitch that is a multiple of 4 doubles keeps every warp
 // store sector-aligned (measured: 36 us vs 54 us per 196 MB for the same store stream, tools/microbench).
@@ -21,12 +27,13 @@
 
 namespace gort {
 
-#define WIDE_STAGE_LINES 256      // lines staged in shared memory per pass (32 KB)
-#define WIDE_NLEAF 11             // omega gam Tff Rff pff tff tpff rs Xf Zf A
+#define WIDE_STAGE_LINES 128      // lines staged in shared memory per pass (16 KB)
+#define WIDE_NLEAF 9              // omega gam Tff Rff pff tff rs Xf A
 
 struct WideArgs {
     int n_sets, n_geom, n_wl, spectra_per_set;
     int chunk;                    // wavelengths per CTA (= LPT * blockDim.x)
+    int pdl;                      // launched with programmatic stream serialization after geom_kernel
     long pitch;                   // output row stride in doubles (>= n_wl)
     long lines_per_cta;
     const double *structure, *lut, *rec, *rleaf, *tleaf, *rsoil;
@@ -39,71 +46,97 @@ rsurf_wide_kernel(const WideArgs a)
 {
     extern __shared__ double2 smem2[];
     double2* srec = smem2;                                                    // [WIDE_STAGE_LINES][8] packed records
-    int* runend = reinterpret_cast<int*>(srec + 8 * WIDE_STAGE_LINES);        // [WIDE_STAGE_LINES]
-    double* leaf = reinterpret_cast<double*>(runend + WIDE_STAGE_LINES);      // [WIDE_NLEAF][chunk]
+    unsigned* runmask = reinterpret_cast<unsigned*>(srec + 8 * WIDE_STAGE_LINES);   // [WIDE_STAGE_LINES / 32] run-start bits
+    double* leaf = reinterpret_cast<double*>(runmask + WIDE_STAGE_LINES / 32);        // [WIDE_NLEAF][chunk]
 
     const long L = (long) a.n_sets * a.n_geom;
     const long line_begin = (long) blockIdx.y * a.lines_per_cta;
     const long line_end = min(L, line_begin + a.lines_per_cta);
-    if (line_begin >= line_end) return;
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int wbase = blockIdx.x * a.chunk;
     const int chunk = a.chunk;
+    // slot j of this thread: column kq + 32*j of the chunk
+    const int kq = (tid >> 5) * (32 * LPT) + (tid & 31);
+    bool ok[LPT];
+#pragma unroll
+    for (int j = 0; j < LPT; j++) ok[j] = (wbase + kq + 32 * j) < a.n_wl;
 
     int m = (int) (line_begin / a.n_geom);
     long set_end = (long) (m + 1) * a.n_geom;                     // first line of the next set
     double k_open = 0.0, ke = 0.0;
+    bool leaf_ready = false;
 
-    double sA[LPT], sPD[LPT], sFCf[LPT], sG[LPT], sZ[LPT], sT[LPT];
+    // (set, lambda) terms of this chunk into shared memory
+    auto fill_leaf = [&](int mm) {
+        const Canopy c = canopy_load(a.structure, a.n_sets, mm, a.lut);
+        k_open = c.k_open; ke = c.k_openep;
+        const size_t sb = a.spectra_per_set ? (size_t) mm * a.n_wl : 0;
+        // this thread's LPT columns: all spectra loads are issued before the first dependent use
+        double rl[LPT], tl[LPT], rs[LPT];
 #pragma unroll
-    for (int j = 0; j < LPT; j++) { sA[j] = sPD[j] = sFCf[j] = sG[j] = sZ[j] = sT[j] = 0.0; }
-    // column of slot j; slots past the end of the spectrum are clamped to the last wavelength: they
-    // recompute and re-store that value (same address, same bits), which keeps the inner loop free of
-    // predicates and branches
-    int wq[LPT];
+        for (int j = 0; j < LPT; j++) {
+            const int w = min(wbase + kq + 32 * j, a.n_wl - 1);
+            rl[j] = a.rleaf[sb + w]; tl[j] = a.tleaf[sb + w]; rs[j] = a.rsoil[sb + w];
+        }
 #pragma unroll
-    for (int j = 0; j < LPT; j++) wq[j] = min(wbase + tid + j * nthr, a.n_wl - 1);   // chunk == LPT * nthr
+        for (int j = 0; j < LPT; j++) {
+            const int k = kq + 32 * j;
+            LeafTerms Lf = leaf_terms(c, rl[j], tl[j], rs[j]);
+            leaf[0 * chunk + k] = Lf.omega; leaf[1 * chunk + k] = Lf.gam; leaf[2 * chunk + k] = Lf.Tff;
+            leaf[3 * chunk + k] = Lf.Rff;   leaf[4 * chunk + k] = Lf.pff; leaf[5 * chunk + k] = Lf.tff;
+            leaf[6 * chunk + k] = Lf.rs;    leaf[7 * chunk + k] = Lf.Xf;  leaf[8 * chunk + k] = Lf.A;
+        }
+    };
+
+    if (line_begin < line_end && a.pdl) {
+        // prologue that does not depend on geom_kernel's output: overlaps with it under PDL
+        fill_leaf(m);
+        leaf_ready = true;
+    }
+    if (a.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (line_begin >= line_end) return;
+
+    double sA[LPT], sP[LPT], sG[LPT], sZ[LPT], sT[LPT];
+    double sPD[SCOMP ? LPT : 1], sFCf[SCOMP ? LPT : 1];
+#pragma unroll
+    for (int j = 0; j < LPT; j++) { sA[j] = sP[j] = sG[j] = sZ[j] = sT[j] = 0.0; }
 
     for (long s0 = line_begin; s0 < line_end; s0 += WIDE_STAGE_LINES) {
         const int nl = (int) min((long) WIDE_STAGE_LINES, line_end - s0);
         __syncthreads();                                          // previous stage fully consumed
-        {   // ---- stage the packed records of lines [s0, s0+nl): 8 double2 per line, coalesced ----
+        {   // ---- stage the packed records of lines [s0, s0+nl): 8 x 16 bytes per line, asynchronous copies
+            //      (LDGSTS) so that every load of the stage is in flight at once ----
             const double2* g = reinterpret_cast<const double2*>(a.rec + (size_t) s0 * GORT_REC_STRIDE);
-            for (int i = tid; i < nl * 8; i += nthr) srec[i] = __ldg(g + i);
+            const unsigned sbase = (unsigned) __cvta_generic_to_shared(srec);
+            for (int i = tid; i < nl * 8; i += nthr)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(sbase + 16u * i), "l"(g + i) : "memory");
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
         __syncthreads();
         // a "run" = a maximal stretch of lines sharing set and sun: starts at line 0 of the stage or at a
-        // flagged line and ends before the next flagged line
-        for (int i = tid; i < nl; i += nthr) {
-            const int f = (int) __double_as_longlong(srec[8 * i + 6].x);
-            if (i == 0 || f != 0) {
-                int e = i + 1;
-                while (e < nl && (int) __double_as_longlong(srec[8 * e + 6].x) == 0) e++;
-                runend[i] = e;
-            }
+        // flagged line and ends before the next flagged line.  One ballot per 32 lines gives the start mask.
+        for (int i0 = (tid >> 5) * 32; i0 < nl; i0 += nthr) {
+            const int i = i0 + (tid & 31);
+            const bool start = i < nl && (int) __double_as_longlong(srec[8 * i + 2].y) != 0;
+            const unsigned bal = __ballot_sync(0xffffffffu, start);
+            if ((tid & 31) == 0) runmask[i0 >> 5] = bal;
         }
         __syncthreads();
 
         int l = 0;
         while (l < nl) {
-            int f = (int) __double_as_longlong(srec[8 * l + 6].x);
+            int f = (int) __double_as_longlong(srec[8 * l + 2].y);
             if (s0 + l == line_begin) f = 3;                      // a CTA's first line starts everything
             if (f & 2) {
-                // ---- new parameter set: (set, lambda) terms of this chunk into shared memory ----
+                // ---- new parameter set ----
                 const long ln = s0 + l;
                 if (ln >= set_end) { m++; set_end += a.n_geom; }  // lines advance one run at a time within a set
-                const Canopy c = canopy_load(a.structure, a.n_sets, m, a.lut);
-                k_open = c.k_open; ke = c.k_openep;
-                const size_t sb = a.spectra_per_set ? (size_t) m * a.n_wl : 0;
-                __syncthreads();                                  // everyone is done reading the old leaf terms
-                for (int k = tid; k < chunk; k += nthr) {
-                    const int w = min(wbase + k, a.n_wl - 1);
-                    LeafTerms Lf = leaf_terms(c, a.rleaf[sb + w], a.tleaf[sb + w], a.rsoil[sb + w]);
-                    leaf[0 * chunk + k] = Lf.omega; leaf[1 * chunk + k] = Lf.gam; leaf[2 * chunk + k] = Lf.Tff;
-                    leaf[3 * chunk + k] = Lf.Rff;   leaf[4 * chunk + k] = Lf.pff; leaf[5 * chunk + k] = Lf.tff;
-                    leaf[6 * chunk + k] = Lf.tpff;  leaf[7 * chunk + k] = Lf.rs;  leaf[8 * chunk + k] = Lf.Xf;
-                    leaf[9 * chunk + k] = Lf.Zf;    leaf[10 * chunk + k] = Lf.A;
+                if (!leaf_ready) {
+                    __syncthreads();                              // everyone is done reading the old leaf terms
+                    fill_leaf(m);
                 }
+                leaf_ready = false;
                 __syncthreads();
             }
             if (f & 1) {
@@ -112,42 +145,60 @@ rsurf_wide_kernel(const WideArgs a)
                 const double2 s0v = srec[8 * l + 4], s1v = srec[8 * l + 5];       // (mus,t0) (tp0,pe_s)
                 Canopy c;
                 c.k_open = k_open; c.k_openep = ke;
+                const double K = k_open + ke;
 #pragma unroll
                 for (int j = 0; j < LPT; j++) {
-                    const int k = tid + j * nthr;                 // < chunk == LPT * nthr
+                    const int k = kq + 32 * j;                    // < chunk
                     LeafTerms Lf;
                     Lf.omega = leaf[0 * chunk + k]; Lf.gam = leaf[1 * chunk + k]; Lf.Tff = leaf[2 * chunk + k];
                     Lf.Rff = leaf[3 * chunk + k];   Lf.pff = leaf[4 * chunk + k]; Lf.tff = leaf[5 * chunk + k];
-                    Lf.tpff = leaf[6 * chunk + k];  Lf.rs = leaf[7 * chunk + k];  Lf.Xf = leaf[8 * chunk + k];
-                    Lf.Zf = leaf[9 * chunk + k];
+                    Lf.rs = leaf[6 * chunk + k];    Lf.Xf = leaf[7 * chunk + k];
+                    Lf.tpff = Lf.tff * (1.0 - K) + K;             // gortt_brdf.c:381-382, as in leaf_terms
+                    Lf.Zf = (Lf.tpff - ke) * Lf.rs;               // gortt.c:492
                     SunTerms S = sun_terms(c, Lf, fd, s0v.x, s0v.y, s1v.x, s1v.y);
-                    sA[j] = leaf[10 * chunk + k];
-                    sPD[j] = S.PD; sFCf[j] = S.FCf; sG[j] = S.G; sZ[j] = S.Z; sT[j] = S.T;
+                    sA[j] = leaf[8 * chunk + k];
+                    sP[j] = S.PDF; sG[j] = S.G; sZ[j] = S.Z; sT[j] = S.T;
+                    if (SCOMP) { sPD[j] = S.PD; sFCf[j] = S.FCf; }
                 }
             }
             // ---- the run: only the view-dependent part per (line, lambda) ----
-            const int e = runend[l];
-            double* out[LPT];
-#pragma unroll
-            for (int j = 0; j < LPT; j++) out[j] = a.rsurf + (size_t) (s0 + l) * a.pitch + wq[j];
+            int e = nl;                                           // first run start after line l
+            for (int wd = l >> 5; wd < (nl + 31) >> 5; wd++) {
+                unsigned mk = runmask[wd];
+                if (wd == (l >> 5)) mk &= (l & 31) == 31 ? 0u : (0xffffffffu << ((l & 31) + 1));
+                if (mk) { e = wd * 32 + __ffs(mk) - 1; break; }
+            }
+            double* out = a.rsurf + (size_t) (s0 + l) * a.pitch + wbase + kq;
             const double2* vr = srec + 8 * l;
-#pragma unroll 2
-            for (; l < e; l++, vr += 8) {
-                const double2 v0 = vr[0], v1 = vr[1], v2 = vr[2], v3 = vr[3];   // (Kc,Kg) (Kt,Kz) (K'g,K'z) (q,fd)
+            if (!SCOMP) {
+#pragma unroll 4
+                for (; l < e; l++, vr += 8, out += a.pitch) {
+                    const double2 v0 = vr[0], v1 = vr[1];          // (cA,Kc) (cG,cZ)
+                    const double cT = vr[2].x;                     // Kt
 #pragma unroll
-                for (int j = 0; j < LPT; j++) {
-                    const double zg = fma(sG[j], v2.x, sZ[j] * v2.y);             // Z*K'z + G*K'g   gortt.c:514
-                    double Cd = fma(sA[j], v3.x, sPD[j]);                         // CdC + CdCG      gortt.c:504-507
-                    Cd = fma(ke, zg, Cd);                                         // + CdG           gortt.c:528
-                    const double C = fma(v3.y, Cd, sFCf[j]);                      // gortt.c:531
-                    const double r = fma(v1.y, sZ[j], fma(v1.x, sT[j], fma(v0.y, sG[j], v0.x * C)));   // gortt.c:557
-                    *out[j] = r;
-                    if (SCOMP) {
-                        double* sc = a.scomp + 4 * (out[j] - a.rsurf);
-                        *reinterpret_cast<double2*>(sc) = make_double2(C, sG[j]);
-                        *reinterpret_cast<double2*>(sc + 2) = make_double2(sT[j], sZ[j]);
+                    for (int j = 0; j < LPT; j++) {
+                        const double r = fma(v0.x, sA[j], fma(v0.y, sP[j], fma(v1.x, sG[j], fma(v1.y, sZ[j], cT * sT[j]))));
+                        if (ok[j]) out[32 * j] = r;
                     }
-                    out[j] += a.pitch;
+                }
+            } else {
+                for (; l < e; l++, vr += 8, out += a.pitch) {
+                    const double Kc = vr[0].y, Kt = vr[2].x;
+                    const double2 v3 = vr[3], v6 = vr[6], v7 = vr[7];   // (q,fd) (K'g,K'z) (Kg,Kz)
+#pragma unroll
+                    for (int j = 0; j < LPT; j++) {
+                        const double zg = fma(sG[j], v6.x, sZ[j] * v6.y);             // Z*K'z + G*K'g   gortt.c:514
+                        double Cd = fma(sA[j], v3.x, sPD[j]);                         // CdC + CdCG      gortt.c:504-507
+                        Cd = fma(ke, zg, Cd);                                         // + CdG           gortt.c:528
+                        const double C = fma(v3.y, Cd, sFCf[j]);                      // gortt.c:531
+                        const double r = fma(v7.y, sZ[j], fma(Kt, sT[j], fma(v7.x, sG[j], Kc * C)));   // gortt.c:557
+                        if (ok[j]) {
+                            out[32 * j] = r;
+                            double* sc = a.scomp + 4 * (size_t) (out + 32 * j - a.rsurf);
+                            *reinterpret_cast<double2*>(sc) = make_double2(C, sG[j]);
+                            *reinterpret_cast<double2*>(sc + 2) = make_double2(sT[j], sZ[j]);
+                        }
+                    }
                 }
             }
         }
