@@ -193,6 +193,14 @@ int launch_brdf(gort_ctx *ctx, cudaStream_t s, const gort_shape &sh, const doubl
     {
         int threads = 32 * GEOM_ROLES;
         long blocks = (L + 31) / 32;
+        // the per-wavelength kernel that follows needs a large shared-memory carve-out; an SM only changes its
+        // carve-out when idle, so ask for the same one here or the dependent kernel's CTAs could not join this
+        // kernel's CTAs on an SM (measured: without it they entered only as geom_kernel's CTAs left)
+        static bool carve_set = false;
+        if (!carve_set) {
+            cudaFuncSetAttribute(geom_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            carve_set = true;
+        }
         geom_kernel<<<(unsigned) blocks, threads, 0, s>>>(sh.n_sets, sh.n_geom, sh.geom_per_set, sh.opt,
                                                           structure, lut, angles, rec, kprop);
         ctx->launches++;
