@@ -319,6 +319,24 @@ class Gort:
                                                   _ptr(angles), _ptr(rleaf), _ptr(tleaf), _ptr(rsoil),
                                                   _ptr(rsurf), _ptr(scomp), _ptr(kprop)))
 
+    def brdf_dev_bind(self, structure, lut, angles, rleaf, tleaf, rsoil, rsurf, scomp=None, kprop=None,
+                      beta=None, fd=None, stream=None):
+        """Same call as brdf_dev with every argument converted once: returns a zero-argument callable that
+        enqueues one gort_brdf_batch_dev (a few microseconds of host time per call instead of the ctypes
+        argument marshalling of brdf_dev).  The tensors are kept alive by the closure."""
+        M = structure.shape[1]
+        G, W = angles.shape[-1], rleaf.shape[-1]
+        sh = self._shape(M, G, W, angles.dim() == 3, rleaf.dim() == 2, beta, fd, out_pitch=rsurf.shape[-1])
+        keep = (structure, lut, angles, rleaf, tleaf, rsoil, rsurf, scomp, kprop, sh)
+        args = (self._h, C.c_void_p(stream), C.byref(sh)) + tuple(C.c_void_p(_ptr(t)) for t in keep[:9])
+        fn, check = self._lib.gort_brdf_batch_dev, self._check
+
+        def call(_keep=keep):
+            rc = fn(*args)
+            if rc:
+                check(rc)
+        return call
+
     def energy_dev(self, structure, lut, angles, rleaf, tleaf, rsoil, albedo, favegt, fasoil,
                    beta=None, fd=None, stream=None):
         M = structure.shape[1]

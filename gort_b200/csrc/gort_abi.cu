@@ -46,6 +46,7 @@ static void *grow(gort_ctx *ctx, void **p, size_t *cap, size_t bytes)
 
 void *scratch(gort_ctx *ctx, int slot, size_t bytes) { return grow(ctx, &ctx->scratch[slot], &ctx->scratch_cap[slot], bytes); }
 void *workspace(gort_ctx *ctx, size_t bytes) { return grow(ctx, &ctx->work, &ctx->work_cap, bytes); }
+void *rec_buffer(gort_ctx *ctx, int which, size_t bytes) { return grow(ctx, &ctx->rec_buf[which], &ctx->rec_cap[which], bytes); }
 
 }  // namespace gort
 
@@ -109,6 +110,9 @@ void gort_destroy(gort_ctx *ctx)
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (int i = 0; i < GORT_NSCRATCH; i++) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
     if (ctx->work) cudaFree(ctx->work);
+    for (int i = 0; i < 2; i++) if (ctx->rec_buf[i]) cudaFree(ctx->rec_buf[i]);
+    if (ctx->d_done) cudaFree(ctx->d_done);
+    if (ctx->xstream_ev) cudaEventDestroy(ctx->xstream_ev);
     if (ctx->d_gauleg) cudaFree(ctx->d_gauleg);
     if (ctx->d_prospect) cudaFree(ctx->d_prospect);
     if (ctx->d_soil) cudaFree(ctx->d_soil);

@@ -149,14 +149,29 @@ static int launch_wide(gort_ctx *ctx, cudaStream_t s, const gort_shape &sh, long
     a.pitch = sh.out_pitch > 0 ? sh.out_pitch : sh.n_wl;
     a.structure = structure; a.lut = lut; a.rec = rec; a.rleaf = rleaf; a.tleaf = tleaf; a.rsoil = rsoil;
     a.rsurf = rsurf; a.scomp = scomp;
+    a.done = ctx->d_done; a.wait_target = ctx->done_expected;
     const size_t smem = sizeof(double2) * 8 * WIDE_STAGE_LINES + sizeof(unsigned) * (WIDE_STAGE_LINES / 32)
                       + sizeof(double) * WIDE_NLEAF * (size_t) a.chunk;
     auto kern = rsurf_wide_kernel<LPT, SCOMP, MINB>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-    if (e != cudaSuccess) return check_cuda(ctx, e, "rsurf_wide_kernel shared memory");
+    // occupancy of this (variant, block size) is looked up once per context
     int occ = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem);
-    if (e != cudaSuccess || occ < 1) occ = 1;
+    for (int i = 0; i < ctx->n_wide_plan; i++) {
+        auto &pl = ctx->wide_plan[i];
+        if (pl.key_lpt == LPT && pl.key_scomp == (int) SCOMP && pl.key_minb == MINB && pl.key_threads == threads) occ = pl.occ;
+    }
+    if (occ == 0) {
+        // allow the largest chunk any block size can ask for (256 threads), so that the attribute never shrinks
+        const size_t smem_max = sizeof(double2) * 8 * WIDE_STAGE_LINES + sizeof(unsigned) * (WIDE_STAGE_LINES / 32)
+                              + sizeof(double) * WIDE_NLEAF * (size_t) LPT * 256;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_max);
+        if (e != cudaSuccess) return check_cuda(ctx, e, "rsurf_wide_kernel shared memory");
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem);
+        if (e != cudaSuccess || occ < 1) occ = 1;
+        if (ctx->n_wide_plan < 8) {
+            auto &pl = ctx->wide_plan[ctx->n_wide_plan++];
+            pl.key_lpt = LPT; pl.key_scomp = (int) SCOMP; pl.key_minb = MINB; pl.key_threads = threads; pl.key_wl = sh.n_wl; pl.occ = occ;
+        }
+    }
     // one resident wave: grid.y contiguous line ranges so that n_chunks * grid.y ~ SMs * occupancy
     long nby = ((long) ctx->sm_count * occ) / n_chunks;
     if (nby < 1) nby = 1;
@@ -173,8 +188,14 @@ static int launch_wide(gort_ctx *ctx, cudaStream_t s, const gort_shape &sh, long
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
-    e = cudaLaunchKernelEx(&cfg, kern, a);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a);
+    if (e == cudaSuccess) ctx->done_expected += (unsigned long long) n_chunks * (unsigned long long) nby;
     return check_cuda(ctx, e, "rsurf_wide_kernel launch");
+}
+
+static bool ranges_overlap(const void *p, const char *lo, const char *hi)
+{
+    return p && lo && (const char *) p >= lo && (const char *) p < hi;
 }
 
 int launch_brdf(gort_ctx *ctx, cudaStream_t s, const gort_shape &sh, const double *structure,
@@ -186,10 +207,37 @@ int launch_brdf(gort_ctx *ctx, cudaStream_t s, const gort_shape &sh, const doubl
     const long L = (long) sh.n_sets * sh.n_geom;
     const long pitch = sh.out_pitch > 0 ? sh.out_pitch : sh.n_wl;
     if (pitch < sh.n_wl) return set_error(ctx, GORT_ERR_INVALID, "gort_brdf: out_pitch smaller than n_wl");
-    double *rec = (double *) workspace(ctx, sizeof(double) * GORT_REC_STRIDE * (size_t) L);
+    static int use_pdl = getenv("GORT_NO_PDL") ? 0 : 1;
+    static int use_xcall = getenv("GORT_NO_XCALL") ? 0 : 1;
+    if (!ctx->d_done) {
+        if (cudaMalloc((void **) &ctx->d_done, sizeof(unsigned long long)) != cudaSuccess)
+            return set_error(ctx, GORT_ERR_NOMEM, "cudaMalloc of the pipeline counter failed");
+        cudaMemset(ctx->d_done, 0, sizeof(unsigned long long));
+        cudaEventCreateWithFlags(&ctx->xstream_ev, cudaEventDisableTiming);
+    }
+    // calls on different streams are ordered one after the other (record buffers and the counter are shared)
+    if (ctx->last_stream && ctx->last_stream != s) {
+        cudaEventRecord(ctx->xstream_ev, ctx->last_stream);
+        cudaStreamWaitEvent(s, ctx->xstream_ev, 0);
+        ctx->last_was_wide = 0;
+    }
+    // line records are double-buffered: this call's geometry kernel may run while the previous call's
+    // per-wavelength kernel still reads its own records
+    ctx->rec_idx ^= 1;
+    double *rec = (double *) rec_buffer(ctx, ctx->rec_idx, sizeof(double) * GORT_REC_STRIDE * (size_t) L);
     if (!rec) return GORT_ERR_NOMEM;
     cudaEvent_t *ev = (ctx->prof_ev && ctx->prof_n < ctx->prof_cap) ? ctx->prof_ev + 3 * ctx->prof_n : NULL;
     if (ev) cudaEventRecord(ev[0], s);
+    // Cross-call overlap: if the previous operation this context put on the stream was a per-wavelength kernel
+    // (which releases its dependents once it is past its start-up), this call's geometry kernel is launched as a
+    // programmatic dependent that never waits: it reads only this call's inputs and writes only the other record
+    // buffer and kprop.  Not done if an input of this call aliases an output of the previous call.
+    bool alias = false;
+    {
+        const void *in[6] = {structure, lut, angles, rleaf, tleaf, rsoil};
+        for (int k = 0; k < 6; k++) for (int r = 0; r < 2; r++) alias |= ranges_overlap(in[k], ctx->last_out_lo[r], ctx->last_out_hi[r]);
+    }
+    const bool early_geom = use_pdl && use_xcall && !ev && ctx->last_was_wide && !alias;
     {
         int threads = 32 * GEOM_ROLES;
         long blocks = (L + 31) / 32;
@@ -201,8 +249,18 @@ int launch_brdf(gort_ctx *ctx, cudaStream_t s, const gort_shape &sh, const doubl
             cudaFuncSetAttribute(geom_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
             carve_set = true;
         }
-        geom_kernel<<<(unsigned) blocks, threads, 0, s>>>(sh.n_sets, sh.n_geom, sh.geom_per_set, sh.opt,
-                                                          structure, lut, angles, rec, kprop);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned) blocks);
+        cfg.blockDim = dim3((unsigned) threads);
+        cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = early_geom ? 1 : 0;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, geom_kernel, sh.n_sets, sh.n_geom, sh.geom_per_set, sh.opt,
+                                           structure, lut, angles, rec, kprop);
+        if (e != cudaSuccess) return check_cuda(ctx, e, "geom_kernel launch");
         ctx->launches++;
     }
     if (ev) cudaEventRecord(ev[1], s);
@@ -210,7 +268,6 @@ int launch_brdf(gort_ctx *ctx, cudaStream_t s, const gort_shape &sh, const doubl
         // tuning knobs (development only): GORT_WIDE_LPT in {2,4}, GORT_WIDE_MINB in {2,3,4}
         static int lpt = getenv("GORT_WIDE_LPT") ? atoi(getenv("GORT_WIDE_LPT")) : 4;
         static int minb = getenv("GORT_WIDE_MINB") ? atoi(getenv("GORT_WIDE_MINB")) : 2;
-        static int use_pdl = getenv("GORT_NO_PDL") ? 0 : 1;
         // programmatic dependent launch: the kernel's (set, lambda) prologue overlaps geom_kernel.  Off while
         // per-kernel events are being recorded (an event between the two launches would time the overlap)
         const bool pdl = use_pdl && !ev;
@@ -232,6 +289,10 @@ int launch_brdf(gort_ctx *ctx, cudaStream_t s, const gort_shape &sh, const doubl
     }
     ctx->launches++;
     if (ev) { cudaEventRecord(ev[2], s); ctx->prof_n++; }
+    ctx->last_stream = s;
+    ctx->last_was_wide = (sh.n_wl >= 64) && !ev;
+    ctx->last_out_lo[0] = (const char *) rsurf; ctx->last_out_hi[0] = (const char *) (rsurf + (size_t) L * pitch);
+    ctx->last_out_lo[1] = (const char *) scomp; ctx->last_out_hi[1] = scomp ? (const char *) (scomp + 4 * (size_t) L * pitch) : NULL;
     return check_cuda(ctx, cudaGetLastError(), "gort_brdf launch");
 }
 

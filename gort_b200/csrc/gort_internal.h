@@ -23,6 +23,19 @@ struct gort_ctx {
     double *d_gauleg;      // [2][32] abscissa, weights          (gauleg, gortt_albedo.c:142-198)
     double *d_prospect;    // [9][2101] refractive,k_Cab,k_Car,k_Anth,k_Brown,k_Cw,k_Cm, tav90, tav40
     double *d_soil;        // [4][421] Price EOF vectors
+    // BRDF pipeline state (gort_brdf.cu): consecutive gort_brdf_batch_dev calls on the same stream overlap
+    // the geometry kernel of call i+1 with the store phase of call i
+    void *rec_buf[2];                  // double-buffered line records
+    size_t rec_cap[2];
+    int rec_idx;
+    unsigned long long *d_done;        // device counter: CTAs of per-wavelength kernels that have finished (cumulative)
+    unsigned long long done_expected;  // host mirror: CTAs launched so far
+    cudaStream_t last_stream;          // stream of the previous BRDF call
+    int last_was_wide;                 // previous BRDF call ended with rsurf_wide_kernel
+    const char *last_out_lo[2], *last_out_hi[2];   // byte ranges of the previous call's rsurf / scomp
+    cudaEvent_t xstream_ev;            // orders BRDF calls issued on different streams
+    struct { int key_lpt, key_scomp, key_minb, key_wl, key_threads; int occ; } wide_plan[8];
+    int n_wide_plan;
     // optional per-kernel event timing of the BRDF path (gort_profile_begin/end)
     cudaEvent_t *prof_ev;  // [3 * prof_cap]
     int prof_cap, prof_n;
@@ -35,6 +48,7 @@ int check_cuda(gort_ctx *ctx, cudaError_t e, const char *what);
 // returns device pointer with at least `bytes` capacity in scratch slot `slot`
 void *scratch(gort_ctx *ctx, int slot, size_t bytes);
 void *workspace(gort_ctx *ctx, size_t bytes);
+void *rec_buffer(gort_ctx *ctx, int which, size_t bytes);
 
 // kernels (device pointers, async on `s`)
 int launch_brdf(gort_ctx *ctx, cudaStream_t s, const gort_shape &sh, const double *structure,

@@ -34,6 +34,8 @@ struct WideArgs {
     int n_sets, n_geom, n_wl, spectra_per_set;
     int chunk;                    // wavelengths per CTA (= LPT * blockDim.x)
     int pdl;                      // launched with programmatic stream serialization after geom_kernel
+    unsigned long long *done;     // cumulative count of finished CTAs of this context's per-wavelength kernels
+    unsigned long long wait_target;   // value of *done once every earlier per-wavelength kernel has finished
     long pitch;                   // output row stride in doubles (>= n_wl)
     long lines_per_cta;
     const double *structure, *lut, *rec, *rleaf, *tleaf, *rsoil;
@@ -94,7 +96,12 @@ rsurf_wide_kernel(const WideArgs a)
         leaf_ready = true;
     }
     if (a.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
-    if (line_begin >= line_end) return;
+    if (line_begin >= line_end) {
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        if (tid == 0) atomicAdd(a.done, 1ull);
+        return;
+    }
+    bool gate_open = false;       // this CTA has not stored anything yet
 
     double sA[LPT], sP[LPT], sG[LPT], sZ[LPT], sT[LPT];
     double sPD[SCOMP ? LPT : 1], sFCf[SCOMP ? LPT : 1];
@@ -161,6 +168,29 @@ rsurf_wide_kernel(const WideArgs a)
                     if (SCOMP) { sPD[j] = S.PD; sFCf[j] = S.FCf; }
                 }
             }
+            if (!gate_open) {
+                // Cross-call pipeline.  Under programmatic dependent launch this CTA may have started while the
+                // previous call's per-wavelength kernel was still storing (possibly to the same output buffer).
+                // Everything up to here touched only inputs, records and registers; before the first store wait
+                // until every CTA of every earlier per-wavelength kernel of this context has finished
+                // (they are all resident or done by the time this kernel can be scheduled, so the wait cannot
+                // deadlock; it is bounded anyway).  Then let the NEXT call's geometry kernel start: it will run
+                // underneath this kernel's store phase.
+                if (tid == 0) {
+                    unsigned long long v, t0 = 0, t1;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+                    for (;;) {
+                        asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(a.done) : "memory");
+                        if (v >= a.wait_target) break;
+                        __nanosleep(200);
+                        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                        if (t1 - t0 > 2000000000ull) break;       // 2 s: never hang on a broken predecessor
+                    }
+                }
+                __syncthreads();
+                asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+                gate_open = true;
+            }
             // ---- the run: only the view-dependent part per (line, lambda) ----
             int e = nl;                                           // first run start after line l
             for (int wd = l >> 5; wd < (nl + 31) >> 5; wd++) {
@@ -203,6 +233,9 @@ rsurf_wide_kernel(const WideArgs a)
             }
         }
     }
+    // publish: all stores of this CTA happen-before the increment (barrier, then fence + atomic by one thread)
+    __syncthreads();
+    if (tid == 0) { __threadfence(); atomicAdd(a.done, 1ull); }
 }
 
 }  // namespace gort
