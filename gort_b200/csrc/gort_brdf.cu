@@ -136,20 +136,25 @@ rsurf_flat_kernel(int n_sets, int n_geom, int n_wl, int spectra_per_set, long pi
 template <int LPT, bool SCOMP, int MINB>
 static int launch_wide(gort_ctx *ctx, cudaStream_t s, const gort_shape &sh, long L, const double *structure,
                        const double *lut, const double *rec, const double *rleaf, const double *tleaf,
-                       const double *rsoil, double *rsurf, double *scomp, bool pdl)
+                       const double *rsoil, double *rsurf, double *scomp, bool pdl, bool gate)
 {
-    // wavelength chunks: as few as possible with <= 256 threads per CTA, lanes spread evenly
-    const int n_chunks = (sh.n_wl + LPT * 256 - 1) / (LPT * 256);
-    int threads = (sh.n_wl + n_chunks * LPT - 1) / (n_chunks * LPT);
+    // columns written per row: the spectrum, plus -- when the caller's pitch leaves room -- the padding up to
+    // the end of the row's last 128-byte line (16 doubles), so that no row ends in a partially written line
+    const long pitch_ = sh.out_pitch > 0 ? sh.out_pitch : sh.n_wl;
+    const int n_col = (int) (pitch_ % 16 == 0 ? ((long) (sh.n_wl + 15) / 16 * 16 < pitch_ ? (long) (sh.n_wl + 15) / 16 * 16 : pitch_) : sh.n_wl);
+    // wavelength chunks: as few as possible with <= WIDE_MAX_THREADS threads per CTA, lanes spread evenly
+    const int n_chunks = (n_col + LPT * WIDE_MAX_THREADS - 1) / (LPT * WIDE_MAX_THREADS);
+    int threads = (n_col + n_chunks * LPT - 1) / (n_chunks * LPT);
     threads = ((threads + 31) / 32) * 32;
     WideArgs a;
     a.n_sets = sh.n_sets; a.n_geom = sh.n_geom; a.n_wl = sh.n_wl; a.spectra_per_set = sh.spectra_per_set;
     a.chunk = LPT * threads;
+    a.n_col = n_col;
     a.pdl = pdl ? 1 : 0;
     a.pitch = sh.out_pitch > 0 ? sh.out_pitch : sh.n_wl;
     a.structure = structure; a.lut = lut; a.rec = rec; a.rleaf = rleaf; a.tleaf = tleaf; a.rsoil = rsoil;
     a.rsurf = rsurf; a.scomp = scomp;
-    a.done = ctx->d_done; a.wait_target = ctx->done_expected;
+    a.done = ctx->d_done;
     const size_t smem = sizeof(double2) * 8 * WIDE_STAGE_LINES + sizeof(unsigned) * (WIDE_STAGE_LINES / 32)
                       + sizeof(double) * WIDE_NLEAF * (size_t) a.chunk;
     auto kern = rsurf_wide_kernel<LPT, SCOMP, MINB>;
@@ -162,7 +167,7 @@ static int launch_wide(gort_ctx *ctx, cudaStream_t s, const gort_shape &sh, long
     if (occ == 0) {
         // allow the largest chunk any block size can ask for (256 threads), so that the attribute never shrinks
         const size_t smem_max = sizeof(double2) * 8 * WIDE_STAGE_LINES + sizeof(unsigned) * (WIDE_STAGE_LINES / 32)
-                              + sizeof(double) * WIDE_NLEAF * (size_t) LPT * 256;
+                              + sizeof(double) * WIDE_NLEAF * (size_t) LPT * WIDE_MAX_THREADS;
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_max);
         if (e != cudaSuccess) return check_cuda(ctx, e, "rsurf_wide_kernel shared memory");
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem);
@@ -173,7 +178,12 @@ static int launch_wide(gort_ctx *ctx, cudaStream_t s, const gort_shape &sh, long
         }
     }
     // one resident wave: grid.y contiguous line ranges so that n_chunks * grid.y ~ SMs * occupancy
-    long nby = ((long) ctx->sm_count * occ) / n_chunks;
+    // one CTA slot per SM is left free (when there are at least two): the next call's CTAs move into it while
+    // this launch is still storing, so their start-up (leaf terms, record staging, sun terms) is off the
+    // store stream's critical path
+    static int spare = getenv("GORT_WIDE_SPARE") ? atoi(getenv("GORT_WIDE_SPARE")) : 0;
+    const int occ_used = (occ > spare) ? occ - spare : occ;
+    long nby = ((long) ctx->sm_count * occ_used) / n_chunks;
     if (nby < 1) nby = 1;
     if (nby > L) nby = L;
     a.lines_per_cta = (L + nby - 1) / nby;
@@ -188,8 +198,13 @@ static int launch_wide(gort_ctx *ctx, cudaStream_t s, const gort_shape &sh, long
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
+    // per-CTA gate: CTA k waits for CTA k of the previous launch when that launch had the same shape and
+    // outputs (then CTA k wrote exactly the region this CTA k is about to write, and the grid is identical
+    // because it is a function of the shape only).  launch_brdf lets a call overlap the previous one only in
+    // that case; otherwise stream order serialises the two and there is nothing to wait for.
+    a.epoch = ++ctx->epoch;
+    a.wait_target = gate ? a.epoch - 1 : 0;
     cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a);
-    if (e == cudaSuccess) ctx->done_expected += (unsigned long long) n_chunks * (unsigned long long) nby;
     return check_cuda(ctx, e, "rsurf_wide_kernel launch");
 }
 
@@ -210,9 +225,9 @@ int launch_brdf(gort_ctx *ctx, cudaStream_t s, const gort_shape &sh, const doubl
     static int use_pdl = getenv("GORT_NO_PDL") ? 0 : 1;
     static int use_xcall = getenv("GORT_NO_XCALL") ? 0 : 1;
     if (!ctx->d_done) {
-        if (cudaMalloc((void **) &ctx->d_done, sizeof(unsigned long long)) != cudaSuccess)
-            return set_error(ctx, GORT_ERR_NOMEM, "cudaMalloc of the pipeline counter failed");
-        cudaMemset(ctx->d_done, 0, sizeof(unsigned long long));
+        if (cudaMalloc((void **) &ctx->d_done, sizeof(unsigned long long) * GORT_MAX_WIDE_CTAS) != cudaSuccess)
+            return set_error(ctx, GORT_ERR_NOMEM, "cudaMalloc of the pipeline flags failed");
+        cudaMemset(ctx->d_done, 0, sizeof(unsigned long long) * GORT_MAX_WIDE_CTAS);
         cudaEventCreateWithFlags(&ctx->xstream_ev, cudaEventDisableTiming);
     }
     // calls on different streams are ordered one after the other (record buffers and the counter are shared)
@@ -237,7 +252,12 @@ int launch_brdf(gort_ctx *ctx, cudaStream_t s, const gort_shape &sh, const doubl
         const void *in[6] = {structure, lut, angles, rleaf, tleaf, rsoil};
         for (int k = 0; k < 6; k++) for (int r = 0; r < 2; r++) alias |= ranges_overlap(in[k], ctx->last_out_lo[r], ctx->last_out_hi[r]);
     }
-    const bool early_geom = use_pdl && use_xcall && !ev && ctx->last_was_wide && !alias;
+    const unsigned long long sig[6] = {(unsigned long long) sh.n_sets, (unsigned long long) sh.n_geom, (unsigned long long) sh.n_wl,
+                                       (unsigned long long) pitch, (unsigned long long) (size_t) rsurf, (unsigned long long) (size_t) scomp};
+    bool same = ctx->last_was_wide != 0;
+    for (int k = 0; k < 6; k++) same &= sig[k] == ctx->last_sig[k];
+    for (int k = 0; k < 6; k++) ctx->last_sig[k] = sig[k];
+    const bool early_geom = use_pdl && use_xcall && !ev && same && !alias;
     {
         int threads = 32 * GEOM_ROLES;
         long blocks = (L + 31) / 32;
@@ -265,19 +285,31 @@ int launch_brdf(gort_ctx *ctx, cudaStream_t s, const gort_shape &sh, const doubl
     }
     if (ev) cudaEventRecord(ev[1], s);
     if (sh.n_wl >= 64) {
-        // tuning knobs (development only): GORT_WIDE_LPT in {2,4}, GORT_WIDE_MINB in {2,3,4}
-        static int lpt = getenv("GORT_WIDE_LPT") ? atoi(getenv("GORT_WIDE_LPT")) : 4;
-        static int minb = getenv("GORT_WIDE_MINB") ? atoi(getenv("GORT_WIDE_MINB")) : 2;
+        // wavelengths per thread: the value in {4, 3, 2} whose chunking wastes the fewest columns (ties: fewer
+        // chunks, then larger LPT).  GORT_WIDE_LPT overrides it (development only).
+        static int lpt_env = getenv("GORT_WIDE_LPT") ? atoi(getenv("GORT_WIDE_LPT")) : 0;
+        int lpt = lpt_env;
+        if (!lpt) {
+            const long pitch_ = pitch;
+            const long n_col = pitch_ % 16 == 0 ? ((long) (sh.n_wl + 15) / 16 * 16 < pitch_ ? (long) (sh.n_wl + 15) / 16 * 16 : pitch_) : sh.n_wl;
+            long best_waste = -1; int best_chunks = 0;
+            for (int cand = 4; cand >= 2; cand--) {
+                const long nc = (n_col + cand * WIDE_MAX_THREADS - 1) / (cand * WIDE_MAX_THREADS);
+                long thr = (n_col + nc * cand - 1) / (nc * cand);
+                thr = (thr + 31) / 32 * 32;
+                const long waste = nc * cand * thr - n_col;
+                if (best_waste < 0 || waste < best_waste || (waste == best_waste && nc < best_chunks)) { best_waste = waste; best_chunks = (int) nc; lpt = cand; }
+            }
+        }
         // programmatic dependent launch: the kernel's (set, lambda) prologue overlaps geom_kernel.  Off while
         // per-kernel events are being recorded (an event between the two launches would time the overlap)
         const bool pdl = use_pdl && !ev;
         int rc;
-#define WIDE_ARGS ctx, s, sh, L, structure, lut, rec, rleaf, tleaf, rsoil, rsurf, scomp, pdl
+#define WIDE_ARGS ctx, s, sh, L, structure, lut, rec, rleaf, tleaf, rsoil, rsurf, scomp, pdl, early_geom
         if (scomp) rc = launch_wide<2, true, 2>(WIDE_ARGS);
-        else if (lpt == 4) rc = (minb <= 2) ? launch_wide<4, false, 2>(WIDE_ARGS) : launch_wide<4, false, 3>(WIDE_ARGS);
-        else if (minb <= 2) rc = launch_wide<2, false, 2>(WIDE_ARGS);
-        else if (minb == 3) rc = launch_wide<2, false, 3>(WIDE_ARGS);
-        else rc = launch_wide<2, false, 4>(WIDE_ARGS);
+        else if (lpt == 4) rc = launch_wide<4, false, 2>(WIDE_ARGS);
+        else if (lpt == 3) rc = launch_wide<3, false, 2>(WIDE_ARGS);
+        else rc = launch_wide<2, false, 2>(WIDE_ARGS);
 #undef WIDE_ARGS
         if (rc != GORT_OK) return rc;
     } else {

@@ -6,6 +6,7 @@
 #include "../../include/gort_b200.h"
 
 #define GORT_NSCRATCH 16
+#define GORT_MAX_WIDE_CTAS 8192
 
 struct gort_ctx {
     int device;
@@ -28,8 +29,9 @@ struct gort_ctx {
     void *rec_buf[2];                  // double-buffered line records
     size_t rec_cap[2];
     int rec_idx;
-    unsigned long long *d_done;        // device counter: CTAs of per-wavelength kernels that have finished (cumulative)
-    unsigned long long done_expected;  // host mirror: CTAs launched so far
+    unsigned long long *d_done;        // [GORT_MAX_WIDE_CTAS] per-CTA epoch of the last per-wavelength launch it finished
+    unsigned long long epoch;          // per-wavelength launches so far
+    unsigned long long last_sig[6];    // grid shape + output identity of the previous per-wavelength launch
     cudaStream_t last_stream;          // stream of the previous BRDF call
     int last_was_wide;                 // previous BRDF call ended with rsurf_wide_kernel
     const char *last_out_lo[2], *last_out_hi[2];   // byte ranges of the previous call's rsurf / scomp

@@ -20,22 +20,28 @@
 //     5 FP64 instructions and one coalesced 8-byte store per evaluation, no branches.
 //     (With scomp requested the crown signature C itself is an output and the long form is used.)
 // HBM traffic is 8 B per evaluation (rsurf) -- the binding roofline for this kernel.
-// Output rows are `pitch` doubles apart; a pitch that is a multiple of 4 doubles keeps every warp
-// store sector-aligned (measured: 36 us vs 54 us per 196 MB for the same store stream, tools/microbench).
+// Output rows are `pitch` doubles apart; a pitch that is a multiple of 16 doubles keeps every warp store
+// line-aligned, and the kernel then also fills the padding columns up to the end of the row's last 128-byte
+// line (with copies of the last column): a row that ends in a partially written line costs the memory system
+// a read-modify-write, measured at 41.6 us vs 37.1 us per 196 MB for the same store stream
+// (tools/microbench/loop_bw.cu, profiles/r1_microbench_loop_bw.txt).
 #pragma once
 #include "gort_device.cuh"
 
 namespace gort {
 
+#define WIDE_MAX_THREADS 384      // largest block the launch heuristic picks
 #define WIDE_STAGE_LINES 128      // lines staged in shared memory per pass (16 KB)
 #define WIDE_NLEAF 9              // omega gam Tff Rff pff tff rs Xf A
 
 struct WideArgs {
     int n_sets, n_geom, n_wl, spectra_per_set;
+    int n_col;                    // columns written per row: n_wl, or up to the end of the row's last 128-byte line when the pitch allows
     int chunk;                    // wavelengths per CTA (= LPT * blockDim.x)
     int pdl;                      // launched with programmatic stream serialization after geom_kernel
-    unsigned long long *done;     // cumulative count of finished CTAs of this context's per-wavelength kernels
-    unsigned long long wait_target;   // value of *done once every earlier per-wavelength kernel has finished
+    unsigned long long *done;     // [grid size] per-CTA epoch: the last launch in which CTA k of this grid shape finished
+    unsigned long long wait_target;   // epoch of the previous launch with the SAME grid shape and outputs (0: nothing to wait for)
+    unsigned long long epoch;         // this launch's epoch
     long pitch;                   // output row stride in doubles (>= n_wl)
     long lines_per_cta;
     const double *structure, *lut, *rec, *rleaf, *tleaf, *rsoil;
@@ -43,7 +49,7 @@ struct WideArgs {
 };
 
 template <int LPT, bool SCOMP, int MINB>
-__global__ void __launch_bounds__(256, MINB)
+__global__ void __launch_bounds__(WIDE_MAX_THREADS, MINB)
 rsurf_wide_kernel(const WideArgs a)
 {
     extern __shared__ double2 smem2[];
@@ -52,6 +58,7 @@ rsurf_wide_kernel(const WideArgs a)
     double* leaf = reinterpret_cast<double*>(runmask + WIDE_STAGE_LINES / 32);        // [WIDE_NLEAF][chunk]
 
     const long L = (long) a.n_sets * a.n_geom;
+    const unsigned cta = blockIdx.y * gridDim.x + blockIdx.x;
     const long line_begin = (long) blockIdx.y * a.lines_per_cta;
     const long line_end = min(L, line_begin + a.lines_per_cta);
     const int tid = threadIdx.x, nthr = blockDim.x;
@@ -61,7 +68,7 @@ rsurf_wide_kernel(const WideArgs a)
     const int kq = (tid >> 5) * (32 * LPT) + (tid & 31);
     bool ok[LPT];
 #pragma unroll
-    for (int j = 0; j < LPT; j++) ok[j] = (wbase + kq + 32 * j) < a.n_wl;
+    for (int j = 0; j < LPT; j++) ok[j] = (wbase + kq + 32 * j) < a.n_col;
 
     int m = (int) (line_begin / a.n_geom);
     long set_end = (long) (m + 1) * a.n_geom;                     // first line of the next set
@@ -98,7 +105,7 @@ rsurf_wide_kernel(const WideArgs a)
     if (a.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
     if (line_begin >= line_end) {
         asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-        if (tid == 0) atomicAdd(a.done, 1ull);
+        if (tid == 0) a.done[cta] = a.epoch;
         return;
     }
     bool gate_open = false;       // this CTA has not stored anything yet
@@ -170,17 +177,18 @@ rsurf_wide_kernel(const WideArgs a)
             }
             if (!gate_open) {
                 // Cross-call pipeline.  Under programmatic dependent launch this CTA may have started while the
-                // previous call's per-wavelength kernel was still storing (possibly to the same output buffer).
-                // Everything up to here touched only inputs, records and registers; before the first store wait
-                // until every CTA of every earlier per-wavelength kernel of this context has finished
-                // (they are all resident or done by the time this kernel can be scheduled, so the wait cannot
-                // deadlock; it is bounded anyway).  Then let the NEXT call's geometry kernel start: it will run
-                // underneath this kernel's store phase.
+                // previous call's per-wavelength kernel was still storing to the same output buffer.  Everything
+                // up to here touched only inputs, records and registers; before the first store wait until the
+                // CTA that owned this very output region in the previous launch (same grid shape, so same index)
+                // has finished.  It is resident or done by the time this kernel can be scheduled, so the wait
+                // cannot deadlock; it is bounded anyway.  Then let the NEXT call's geometry kernel start: it runs
+                // underneath this kernel's store phase, and by then every CTA of the previous launch is done, so
+                // the record buffer it overwrites is free.
                 if (tid == 0) {
                     unsigned long long v, t0 = 0, t1;
                     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
                     for (;;) {
-                        asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(a.done) : "memory");
+                        asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(a.done + cta) : "memory");
                         if (v >= a.wait_target) break;
                         __nanosleep(200);
                         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
@@ -235,7 +243,7 @@ rsurf_wide_kernel(const WideArgs a)
     }
     // publish: all stores of this CTA happen-before the increment (barrier, then fence + atomic by one thread)
     __syncthreads();
-    if (tid == 0) { __threadfence(); atomicAdd(a.done, 1ull); }
+    if (tid == 0) { __threadfence(); asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(a.done + cta), "l"(a.epoch) : "memory"); }
 }
 
 }  // namespace gort

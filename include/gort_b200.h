@@ -72,8 +72,11 @@ typedef struct {
     int spectra_per_set;   /* 0: rleaf/tleaf/rsoil are [W]; 1: [M][W] */
     gort_options opt;
     int out_pitch;         /* row stride, in doubles, of rsurf (and, x4, of scomp); 0 = n_wl (dense).
-                              A multiple of 4 keeps every warp store 32-byte aligned in HBM: the same
-                              store stream runs ~1.4x faster than with an odd stride such as 2101 */
+                              A multiple of 16 keeps every row 128-byte aligned in HBM; the padding columns
+                              [n_wl, min(out_pitch, round_up(n_wl, 16))) then belong to the call and receive
+                              copies of column n_wl-1, so that no row ends in a partially written line (the
+                              same store stream runs 1.12x faster; an odd stride such as 2101 costs 1.5x).
+                              Columns beyond that are never touched. */
 } gort_shape;
 
 /* ---- context ---------------------------------------------------------------------------- */

@@ -292,9 +292,25 @@ def test_c2_full_size_properties(gort, oracle):
     gort.brdf_dev(t(st), t(lut), t(ang), t(rl[0]), t(tl[0]), t(rs[0]), out)
     gort.synchronize()
     assert np.array_equal(out.cpu().numpy(), rsurf)
-    # padded row pitch (aligned warp stores): same bits in the first W columns, padding untouched
+    # padded row pitch (line-aligned warp stores): same bits in the first W columns; the padding up to the end
+    # of the row's last 128-byte line belongs to the call and receives copies of the last column
     outp = torch.full((1, 11664, 2112), -7.0, dtype=torch.float64, device=dev)
     gort.brdf_dev(t(st), t(lut), t(ang), t(rl[0]), t(tl[0]), t(rs[0]), outp)
     gort.synchronize()
     hp = outp.cpu().numpy()
-    assert np.array_equal(hp[:, :, :2101], rsurf) and np.all(hp[:, :, 2101:] == -7.0)
+    assert np.array_equal(hp[:, :, :2101], rsurf) and np.array_equal(hp[:, :, 2101:], np.repeat(rsurf[:, :, 2100:], 11, axis=2))
+    # a pitch beyond that line: the extra columns are not touched
+    outq = torch.full((1, 64, 2144), -7.0, dtype=torch.float64, device=dev)
+    gort.brdf_dev(t(st), t(lut), t(ang[:, :64]), t(rl[0]), t(tl[0]), t(rs[0]), outq)
+    gort.synchronize()
+    hq = outq.cpu().numpy()
+    assert np.array_equal(hq[:, :, :2101], rsurf[:, :64]) and np.all(hq[:, :, 2112:] == -7.0)
+    # repeated calls into the same buffer overlap across calls (geometry kernel of call i+1 under the stores of
+    # call i): results must still be those of the last call
+    ang2 = ang.copy(); ang2[0] = (ang2[0] + 2.5) % 85.0
+    d_a1, d_a2 = t(ang), t(ang2)
+    for k in range(6):
+        gort.brdf_dev(t(st), t(lut), d_a2 if k % 2 else d_a1, t(rl[0]), t(tl[0]), t(rs[0]), outp)
+    gort.synchronize()
+    ref2 = gort.brdf(st, lut, ang2, rl[0], tl[0], rs[0])
+    assert np.array_equal(outp.cpu().numpy()[:, :, :2101], ref2)
