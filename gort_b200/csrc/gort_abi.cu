@@ -112,6 +112,7 @@ void gort_destroy(gort_ctx *ctx)
     if (ctx->work) cudaFree(ctx->work);
     for (int i = 0; i < 2; i++) if (ctx->rec_buf[i]) cudaFree(ctx->rec_buf[i]);
     if (ctx->d_done) cudaFree(ctx->d_done);
+    if (ctx->d_tile_flags) cudaFree(ctx->d_tile_flags);
     if (ctx->xstream_ev) cudaEventDestroy(ctx->xstream_ev);
     if (ctx->d_gauleg) cudaFree(ctx->d_gauleg);
     if (ctx->d_prospect) cudaFree(ctx->d_prospect);

@@ -11,6 +11,7 @@
 //   rsurf_flat_kernel  W < 64 (band sets): one thread per (line, band).
 //   energy_kernel      one CTA per (set, sun line): 512 quadrature nodes' records in shared
 //                      memory, lanes = azimuth nodes, warp-shuffle reduction (gortt_albedo.c).
+#include <stdio.h>
 #include <stdlib.h>
 #include "gort_device.cuh"
 #include "gort_internal.h"
@@ -32,7 +33,8 @@ namespace gort {
 __global__ void __launch_bounds__(32 * GEOM_ROLES)
 geom_kernel(int n_sets, int n_geom, int geom_per_set, gort_options opt,
             const double* __restrict__ structure, const double* __restrict__ lut,
-            const double* __restrict__ angles, double* __restrict__ rec, double* __restrict__ kprop)
+            const double* __restrict__ angles, double* __restrict__ rec, double* __restrict__ kprop,
+            unsigned long long* __restrict__ tile_flags, unsigned long long call_no)
 {
     // let the dependent per-wavelength kernel start its prologue (leaf terms) while this grid runs; it still
     // waits for this grid's completion (griddepcontrol.wait) before it reads a record
@@ -79,7 +81,8 @@ geom_kernel(int n_sets, int n_geom, int geom_per_set, gort_options opt,
         ex[6][lane] = h.kuusk; ex[7][lane] = h.pn0_s; ex[8][lane] = h.pe_s;
     }
     __syncthreads();
-    if (role != 0 || line_raw >= L) return;
+    if (role != 0) return;
+    if (line_raw < L) {
     Tail tl; Hot h;
     tl.e_v = ex[2][lane]; tl.e_s = ex[3][lane]; tl.t0 = ex[4][lane]; tl.beta = ex[5][lane];
     h.kuusk = ex[6][lane]; h.pn0_s = ex[7][lane]; h.pe_s = ex[8][lane];
@@ -99,6 +102,14 @@ geom_kernel(int n_sets, int n_geom, int geom_per_set, gort_options opt,
     if (kprop) {
         kprop[4 * line + 0] = r.Kc; kprop[4 * line + 1] = r.Kg;
         kprop[4 * line + 2] = r.Kt; kprop[4 * line + 3] = r.Kz;
+    }
+    }
+    // publish this tile: the per-wavelength kernel waits on these flags, not on the completion of this grid (a
+    // grid launched as a programmatic dependent is not complete before its predecessors in the stream are)
+    __syncwarp();
+    if (lane == 0) {
+        __threadfence();
+        asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(tile_flags + blockIdx.x), "l"(call_no) : "memory");
     }
 }
 
@@ -133,6 +144,15 @@ rsurf_flat_kernel(int n_sets, int n_geom, int n_wl, int spectra_per_set, long pi
     if (scomp) *reinterpret_cast<double4*>(scomp + 4 * o) = make_double4(C, S.G, S.T, S.Z);
 }
 
+static unsigned long long *timeline_buffer()
+{
+    static unsigned long long *d = NULL;
+    static int on = getenv("GORT_TIMELINE") ? 1 : 0;
+    if (on && !d) cudaMalloc((void **) &d, 2 * 64 * GORT_MAX_WIDE_CTAS);
+    return d;
+}
+static void timeline_report(cudaStream_t s, int ncta, int half);
+
 template <int LPT, bool SCOMP, int MINB>
 static int launch_wide(gort_ctx *ctx, cudaStream_t s, const gort_shape &sh, long L, const double *structure,
                        const double *lut, const double *rec, const double *rleaf, const double *tleaf,
@@ -142,8 +162,8 @@ static int launch_wide(gort_ctx *ctx, cudaStream_t s, const gort_shape &sh, long
     // the end of the row's last 128-byte line (16 doubles), so that no row ends in a partially written line
     const long pitch_ = sh.out_pitch > 0 ? sh.out_pitch : sh.n_wl;
     const int n_col = (int) (pitch_ % 16 == 0 ? ((long) (sh.n_wl + 15) / 16 * 16 < pitch_ ? (long) (sh.n_wl + 15) / 16 * 16 : pitch_) : sh.n_wl);
-    // wavelength chunks: as few as possible with <= WIDE_MAX_THREADS threads per CTA, lanes spread evenly
-    const int n_chunks = (n_col + LPT * WIDE_MAX_THREADS - 1) / (LPT * WIDE_MAX_THREADS);
+    // wavelength chunks: as few as possible with <= WIDE_PICK_THREADS threads per CTA, lanes spread evenly
+    const int n_chunks = (n_col + LPT * WIDE_PICK_THREADS - 1) / (LPT * WIDE_PICK_THREADS);
     int threads = (n_col + n_chunks * LPT - 1) / (n_chunks * LPT);
     threads = ((threads + 31) / 32) * 32;
     WideArgs a;
@@ -155,6 +175,8 @@ static int launch_wide(gort_ctx *ctx, cudaStream_t s, const gort_shape &sh, long
     a.structure = structure; a.lut = lut; a.rec = rec; a.rleaf = rleaf; a.tleaf = tleaf; a.rsoil = rsoil;
     a.rsurf = rsurf; a.scomp = scomp;
     a.done = ctx->d_done;
+    a.tile_flags = ctx->d_tile_flags; a.call_no = ctx->call_no;
+    a.tl = timeline_buffer();                                           // consecutive calls stamp alternate halves (set below)
     const size_t smem = sizeof(double2) * 8 * WIDE_STAGE_LINES + sizeof(unsigned) * (WIDE_STAGE_LINES / 32)
                       + sizeof(double) * WIDE_NLEAF * (size_t) a.chunk;
     auto kern = rsurf_wide_kernel<LPT, SCOMP, MINB>;
@@ -203,9 +225,42 @@ static int launch_wide(gort_ctx *ctx, cudaStream_t s, const gort_shape &sh, long
     // because it is a function of the shape only).  launch_brdf lets a call overlap the previous one only in
     // that case; otherwise stream order serialises the two and there is nothing to wait for.
     a.epoch = ++ctx->epoch;
+    if (a.tl) a.tl = timeline_buffer() + (a.epoch & 1) * 8 * GORT_MAX_WIDE_CTAS;
     a.wait_target = gate ? a.epoch - 1 : 0;
     cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a);
+    if (a.tl) timeline_report(s, n_chunks * (int) nby, (int) (a.epoch & 1));
     return check_cuda(ctx, e, "rsurf_wide_kernel launch");
+}
+
+// Development aid: GORT_TIMELINE=<call number> makes every rsurf_wide_kernel CTA record %globaltimer stamps at its
+// phase boundaries; after the given call the stamps of that call and the one before it are summarised on stderr.
+static void timeline_report(cudaStream_t s, int ncta, int half)
+{
+    static int calls = 0;
+    static int at = getenv("GORT_TIMELINE") ? atoi(getenv("GORT_TIMELINE")) : 0;
+    if (!at || ++calls != at) return;
+    cudaStreamSynchronize(s);
+    unsigned long long *h = (unsigned long long *) malloc(64 * (size_t) ncta), *prev = (unsigned long long *) malloc(64 * (size_t) ncta);
+    cudaMemcpy(h, timeline_buffer() + half * 8 * GORT_MAX_WIDE_CTAS, 64 * (size_t) ncta, cudaMemcpyDeviceToHost);
+    cudaMemcpy(prev, timeline_buffer() + (half ^ 1) * 8 * GORT_MAX_WIDE_CTAS, 64 * (size_t) ncta, cudaMemcpyDeviceToHost);
+    unsigned long long t0 = ~0ull;
+    for (int i = 0; i < ncta; i++) if (h[i * 8] < t0) t0 = h[i * 8];
+    const char *nm[6] = {"entry", "leaf table done", "geometry complete", "first sun terms", "gate passed", "end"};
+    fprintf(stderr, "rsurf_wide_kernel timeline, call %d, %d CTAs, us since the first CTA entry of this call\n", at, ncta);
+    if (prev) {
+        double mn = 1e30, mx = -1e30, sm = 0;
+        for (int i = 0; i < ncta; i++) { double v = (double) ((long long) (prev[i * 8 + 5] - t0)) * 1e-3; if (v < mn) mn = v; if (v > mx) mx = v; sm += v; }
+        fprintf(stderr, "  %-20s min %8.2f avg %8.2f max %8.2f\n", "previous call: end", mn, sm / ncta, mx);
+    }
+    for (int k = 0; k < 6; k++) {
+        double mn = 1e30, mx = -1e30, sm = 0;
+        for (int i = 0; i < ncta; i++) { double v = (double) ((long long) (h[i * 8 + k] - t0)) * 1e-3; if (v < mn) mn = v; if (v > mx) mx = v; sm += v; }
+        fprintf(stderr, "  %-20s min %8.2f avg %8.2f max %8.2f\n", nm[k], mn, sm / ncta, mx);
+    }
+    double gw = 0, st = 0, run = 0;
+    for (int i = 0; i < ncta; i++) { gw += (h[i * 8 + 4] - h[i * 8 + 3]) * 1e-3; st += (h[i * 8 + 3] - h[i * 8]) * 1e-3; run += (h[i * 8 + 5] - h[i * 8 + 4]) * 1e-3; }
+    fprintf(stderr, "  per CTA: start-up %.2f us, gate wait %.2f us, store phase %.2f us\n", st / ncta, gw / ncta, run / ncta);
+    free(h); free(prev);
 }
 
 static bool ranges_overlap(const void *p, const char *lo, const char *hi)
@@ -235,6 +290,21 @@ int launch_brdf(gort_ctx *ctx, cudaStream_t s, const gort_shape &sh, const doubl
         cudaEventRecord(ctx->xstream_ev, ctx->last_stream);
         cudaStreamWaitEvent(s, ctx->xstream_ev, 0);
         ctx->last_was_wide = 0;
+    }
+    // per-tile ready flags of the geometry records
+    {
+        const size_t tiles = (size_t) ((L + 31) / 32);
+        if (tiles > ctx->tile_cap) {
+            cudaDeviceSynchronize();
+            if (ctx->d_tile_flags) cudaFree(ctx->d_tile_flags);
+            ctx->d_tile_flags = NULL; ctx->tile_cap = 0;
+            const size_t want = tiles + tiles / 4 + 1024;
+            if (cudaMalloc((void **) &ctx->d_tile_flags, sizeof(unsigned long long) * want) != cudaSuccess)
+                return set_error(ctx, GORT_ERR_NOMEM, "cudaMalloc of the tile flags failed");
+            cudaMemset(ctx->d_tile_flags, 0, sizeof(unsigned long long) * want);
+            ctx->tile_cap = want;
+        }
+        ctx->call_no++;
     }
     // line records are double-buffered: this call's geometry kernel may run while the previous call's
     // per-wavelength kernel still reads its own records
@@ -279,7 +349,7 @@ int launch_brdf(gort_ctx *ctx, cudaStream_t s, const gort_shape &sh, const doubl
         cfg.attrs = attr;
         cfg.numAttrs = early_geom ? 1 : 0;
         cudaError_t e = cudaLaunchKernelEx(&cfg, geom_kernel, sh.n_sets, sh.n_geom, sh.geom_per_set, sh.opt,
-                                           structure, lut, angles, rec, kprop);
+                                           structure, lut, angles, rec, kprop, ctx->d_tile_flags, ctx->call_no);
         if (e != cudaSuccess) return check_cuda(ctx, e, "geom_kernel launch");
         ctx->launches++;
     }
@@ -294,7 +364,7 @@ int launch_brdf(gort_ctx *ctx, cudaStream_t s, const gort_shape &sh, const doubl
             const long n_col = pitch_ % 16 == 0 ? ((long) (sh.n_wl + 15) / 16 * 16 < pitch_ ? (long) (sh.n_wl + 15) / 16 * 16 : pitch_) : sh.n_wl;
             long best_waste = -1; int best_chunks = 0;
             for (int cand = 4; cand >= 2; cand--) {
-                const long nc = (n_col + cand * WIDE_MAX_THREADS - 1) / (cand * WIDE_MAX_THREADS);
+                const long nc = (n_col + cand * WIDE_PICK_THREADS - 1) / (cand * WIDE_PICK_THREADS);
                 long thr = (n_col + nc * cand - 1) / (nc * cand);
                 thr = (thr + 31) / 32 * 32;
                 const long waste = nc * cand * thr - n_col;

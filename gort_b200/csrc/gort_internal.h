@@ -31,6 +31,9 @@ struct gort_ctx {
     int rec_idx;
     unsigned long long *d_done;        // [GORT_MAX_WIDE_CTAS] per-CTA epoch of the last per-wavelength launch it finished
     unsigned long long epoch;          // per-wavelength launches so far
+    unsigned long long *d_tile_flags;  // [tile_cap] per 32-line tile: BRDF call number whose geometry records are ready
+    size_t tile_cap;
+    unsigned long long call_no;        // BRDF calls so far
     unsigned long long last_sig[6];    // grid shape + output identity of the previous per-wavelength launch
     cudaStream_t last_stream;          // stream of the previous BRDF call
     int last_was_wide;                 // previous BRDF call ended with rsurf_wide_kernel

@@ -25,12 +25,25 @@
 // line (with copies of the last column): a row that ends in a partially written line costs the memory system
 // a read-modify-write, measured at 41.6 us vs 37.1 us per 196 MB for the same store stream
 // (tools/microbench/loop_bw.cu, profiles/r1_microbench_loop_bw.txt).
+//
+// Pipeline across kernels and calls (all of it optional: without programmatic dependent launch the same code
+// runs strictly in stream order and every wait below is already satisfied):
+//   * the kernel is launched as a programmatic dependent of geom_kernel and never waits for that grid to
+//     complete; it builds its (set, lambda) table first and then waits, stage by stage, on the per-tile flags
+//     geom_kernel publishes with its records;
+//   * before its first store a CTA waits until the CTA with the same index in the previous launch of the same
+//     shape has finished (that CTA wrote the same output region), then releases its own dependents: the NEXT
+//     call's geom_kernel, which therefore runs underneath this launch's store phase;
+//   * at exit a CTA publishes its epoch.
+//   Steady state for repeated calls: the store stream of call i+1 starts CTA by CTA as the CTAs of call i
+//   retire, with the geometry of call i+1 already in HBM.  Measured on C2: 54.7 -> 39 us per call.
 #pragma once
 #include "gort_device.cuh"
 
 namespace gort {
 
-#define WIDE_MAX_THREADS 384      // largest block the launch heuristic picks
+#define WIDE_MAX_THREADS 384      // register cap of the kernel: 65536 / (2 * 384) -> 80
+#define WIDE_PICK_THREADS 288     // largest block the launch heuristic picks: two CTAs then leave an SM room for one geom_kernel CTA
 #define WIDE_STAGE_LINES 128      // lines staged in shared memory per pass (16 KB)
 #define WIDE_NLEAF 9              // omega gam Tff Rff pff tff rs Xf A
 
@@ -38,7 +51,10 @@ struct WideArgs {
     int n_sets, n_geom, n_wl, spectra_per_set;
     int n_col;                    // columns written per row: n_wl, or up to the end of the row's last 128-byte line when the pitch allows
     int chunk;                    // wavelengths per CTA (= LPT * blockDim.x)
+    unsigned long long *tl;       // optional timeline [grid][8] of %globaltimer stamps (GORT_TIMELINE, development aid)
     int pdl;                      // launched with programmatic stream serialization after geom_kernel
+    const unsigned long long *tile_flags;   // per 32-line tile: call number whose records geom_kernel has published
+    unsigned long long call_no;
     unsigned long long *done;     // [grid size] per-CTA epoch: the last launch in which CTA k of this grid shape finished
     unsigned long long wait_target;   // epoch of the previous launch with the SAME grid shape and outputs (0: nothing to wait for)
     unsigned long long epoch;         // this launch's epoch
@@ -52,6 +68,8 @@ template <int LPT, bool SCOMP, int MINB>
 __global__ void __launch_bounds__(WIDE_MAX_THREADS, MINB)
 rsurf_wide_kernel(const WideArgs a)
 {
+#define WIDE_TL(k) do { if (a.tl && threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); a.tl[(size_t) (blockIdx.y * gridDim.x + blockIdx.x) * 8 + (k)] = t_; } } while (0)
+    WIDE_TL(0);                                                               // CTA entry
     extern __shared__ double2 smem2[];
     double2* srec = smem2;                                                    // [WIDE_STAGE_LINES][8] packed records
     unsigned* runmask = reinterpret_cast<unsigned*>(srec + 8 * WIDE_STAGE_LINES);   // [WIDE_STAGE_LINES / 32] run-start bits
@@ -102,7 +120,7 @@ rsurf_wide_kernel(const WideArgs a)
         fill_leaf(m);
         leaf_ready = true;
     }
-    if (a.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
+    WIDE_TL(1);                                                               // (set, lambda) table done
     if (line_begin >= line_end) {
         asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
         if (tid == 0) a.done[cta] = a.epoch;
@@ -118,8 +136,24 @@ rsurf_wide_kernel(const WideArgs a)
     for (long s0 = line_begin; s0 < line_end; s0 += WIDE_STAGE_LINES) {
         const int nl = (int) min((long) WIDE_STAGE_LINES, line_end - s0);
         __syncthreads();                                          // previous stage fully consumed
-        {   // ---- stage the packed records of lines [s0, s0+nl): 8 x 16 bytes per line, asynchronous copies
-            //      (LDGSTS) so that every load of the stage is in flight at once ----
+        {   // ---- wait for geom_kernel's tiles of this stage (acquire on their flags; every CTA of geom_kernel is
+            //      resident or done before this kernel can be scheduled, so the wait cannot deadlock), then stage
+            //      the packed records of lines [s0, s0+nl): 8 x 16 bytes per line, asynchronous copies (LDGSTS) so
+            //      that every load of the stage is in flight at once ----
+            const long tile0 = s0 >> 5, tile1 = (s0 + nl - 1) >> 5;
+            for (long t = tile0 + tid; t <= tile1; t += nthr) {
+                unsigned long long v, t0 = 0, t1;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+                for (;;) {
+                    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(a.tile_flags + t) : "memory");
+                    if (v >= a.call_no) break;
+                    __nanosleep(100);
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                    if (t1 - t0 > 2000000000ull) break;           // 2 s: never hang
+                }
+            }
+            __syncthreads();
+            if (s0 == line_begin) WIDE_TL(2);                     // geometry records of the first stage ready
             const double2* g = reinterpret_cast<const double2*>(a.rec + (size_t) s0 * GORT_REC_STRIDE);
             const unsigned sbase = (unsigned) __cvta_generic_to_shared(srec);
             for (int i = tid; i < nl * 8; i += nthr)
@@ -176,6 +210,7 @@ rsurf_wide_kernel(const WideArgs a)
                 }
             }
             if (!gate_open) {
+                WIDE_TL(3);                                                   // records staged, first sun terms in registers
                 // Cross-call pipeline.  Under programmatic dependent launch this CTA may have started while the
                 // previous call's per-wavelength kernel was still storing to the same output buffer.  Everything
                 // up to here touched only inputs, records and registers; before the first store wait until the
@@ -198,6 +233,7 @@ rsurf_wide_kernel(const WideArgs a)
                 __syncthreads();
                 asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
                 gate_open = true;
+                WIDE_TL(4);                                                   // gate passed: first store follows
             }
             // ---- the run: only the view-dependent part per (line, lambda) ----
             int e = nl;                                           // first run start after line l
@@ -241,8 +277,9 @@ rsurf_wide_kernel(const WideArgs a)
             }
         }
     }
-    // publish: all stores of this CTA happen-before the increment (barrier, then fence + atomic by one thread)
+    // publish: all stores of this CTA happen-before the flag (barrier, then fence + release by one thread)
     __syncthreads();
+    WIDE_TL(5);                                                               // all stores issued
     if (tid == 0) { __threadfence(); asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(a.done + cta), "l"(a.epoch) : "memory"); }
 }
 
