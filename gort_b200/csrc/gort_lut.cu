@@ -15,6 +15,10 @@
 // exp(-s_bin tau') pd_s[bin] is accumulated entry by entry with the entry's bin index, which is
 // the same sum in a different association (differences ~1e-16 relative).
 //
+// Code size matters here: with everything inlined and the Simpson loops unrolled the kernel was 18 000 SASS
+// instructions and its top stall was instruction fetch (stall_no_instruction ~70 % of samples in the geometry
+// code, ncu profiles/r1_lut).  The geometry helpers are therefore __noinline__ and their loops not unrolled.
+//
 // Parity hazards honoured: no FMA contraction (r*r - h2*h2 must be exactly
 // 0 when h2 == r), running-sum loop counters (z += dz_p, h += dh), (int)(s/ds + 0.5) binning,
 // the |a3| < 1e-10 clamp, float-typed Simpson factors.
@@ -58,7 +62,7 @@ __device__ __forceinline__ double right_ellipse_area(double r, double b, double 
 }
 
 // gortt_pn_kopen.c:170-229 with the "weird" section :233-282 inlined
-__device__ double cross_section(const Crown& c, const Ang& a, double h, double z)
+__device__ __noinline__ double cross_section(const Crown& c, const Ang& a, double h, double z)
 {
     if (z < h - c.r) return 0.0;
     double h_low = h - c.r * a.s;
@@ -80,7 +84,7 @@ __device__ double cross_section(const Crown& c, const Ang& a, double h, double z
 }
 
 // gortt_pn_kopen.c:149-167
-__device__ double proj_volume(const Crown& c, const Ang& a, double h)
+__device__ __noinline__ double proj_volume(const Crown& c, const Ang& a, double h)
 {
     double vol = 0.0;
     int guard = 0;
@@ -100,7 +104,7 @@ __device__ __forceinline__ double triang_fcn(double x, double b, double r, doubl
 }
 
 // gortt_pn_kopen.c:811-854
-__device__ double triang(double b, double r, const Ang& a)
+__device__ __noinline__ double triang(double b, double r, const Ang& a)
 {
     double sint = a.s, cost = a.c;
     double a1 = r * r - b * b * sint * sint;
@@ -108,9 +112,11 @@ __device__ double triang(double b, double r, const Ang& a)
     const int m = LUT_NOINT;
     double h = .50 * (x0 - b) / (double) (float) m;
     double sum1 = 0.0;
+#pragma unroll 1
     for (int i = 0; i < m; i++) sum1 += triang_fcn(b + (double) (float) (2 * i + 1) * h, b, r, a.t);
     double volume = 4.0 * sum1;
     double sum2 = 0.0;
+#pragma unroll 1
     for (int i = 0; i < m - 1; i++) sum2 += triang_fcn(b + (double) (float) (2 * (i + 1)) * h, b, r, a.t);
     volume += 2.0 * sum2;
     volume += triang_fcn(x0, b, r, a.t);
@@ -128,7 +134,7 @@ __device__ __forceinline__ double sector(double a1, double a2, double r)
 }
 
 // gortt_pn_kopen.c:771-792
-__device__ double trisec(double hh, double hh_b, const Ang& a, double r)
+__device__ __noinline__ double trisec(double hh, double hh_b, const Ang& a, double r)
 {
     double tmp = (hh - hh_b);
     double x = -1.0 * tmp * a.s + sqrt(r * r - tmp * tmp) * a.c;
@@ -143,7 +149,7 @@ __device__ __forceinline__ double cylind_fcn(double x, double r)
 }
 
 // gortt_pn_kopen.c:891-924
-__device__ double cylind(double r, double h1, double h2, double h)
+__device__ __noinline__ double cylind(double r, double h1, double h2, double h)
 {
     double slope = h / (h2 - h1);
     double tmp1 = sqrt(r * r - h1 * h1);
@@ -162,7 +168,7 @@ __device__ double cylind(double r, double h1, double h2, double h)
 }
 
 // gortt_pn_kopen.c:665-768; hp_h = height_p[h], hp_s = height_p[h_s]
-__device__ double tube_vol(const Crown& c, const Ang& a, double hp_h, double hp_s, double h_b)
+__device__ __noinline__ double tube_vol(const Crown& c, const Ang& a, double hp_h, double hp_s, double h_b)
 {
     const double r = c.r;
     double V, V_sp1, V_sp2, V_cyln, h_t, h_tt;
@@ -215,7 +221,7 @@ __device__ double tube_vol(const Crown& c, const Ang& a, double hp_h, double hp_
 }
 
 // gortt_pn_kopen.c:566-645; hz = height_p[z]
-__device__ double mean_single_crown_path(const Crown& c, const Ang& a, double hz, double h)
+__device__ __noinline__ double mean_single_crown_path(const Crown& c, const Ang& a, double hz, double h)
 {
     if (hz > h + c.r - 0.0001) return 0.0;
     if (hz < h - c.r + 0.0001) return 4.0 * c.r / 3.0;
@@ -242,6 +248,26 @@ __device__ double expected_single_crown_path(const Crown& c, const Ang& a, doubl
     return ES;
 }
 
+// lut_full_kernel: one CTA per GROUP of consecutive parameter sets that share (r, b, h1, h2) bit for bit
+// (capped at LUT_GROUP_CAP sets, chunk boundaries at multiples of the cap), one thread per zenith index t.
+//   phase 1, once per group: everything that depends on crown shape and zenith only -- the projected
+//            cross-section volumes v_g[h][t] (gortt_pn_kopen.c:24-32, :149-323), E[S] (:534-563), and for every
+//            entry height the tube-volume difference of :496 (Simpson rule, sphere/cylinder sections);
+//   phase 2, per member: p_n0 = exp(-lv' v_g) (stem density), the crown-count loop (:489-527) and the
+//            within-crown gap sum (favd), then the trapezoid rule of gortt_calc_kopen by thread 0.
+// Phase 1 is ~2/3 of a set's instructions, so LUT grids and ensembles that vary stem density / leaf area over
+// fixed crown shapes (BASELINE.json configs 4a and 5) pay it once per group instead of once per set.
+#define LUT_GROUP_CAP 64
+// 1/n!, n = 0..30 (the reference tabulates n! in gortt.c:752-754 and divides)
+__constant__ double c_inv_fact[LUT_MAXCROWNS + 1];
+#define LUT_NSP (GORT_NLAYERS - 2)     // entry heights sp_i = 1 .. 13 (sp_i = 14 contributes p_s0 = 0)
+
+__device__ __forceinline__ bool same_shape(const double* __restrict__ st, size_t n, int a, int b)
+{
+    return st[1 * n + a] == st[1 * n + b] && st[2 * n + a] == st[2 * n + b] &&
+           st[3 * n + a] == st[3 * n + b] && st[4 * n + a] == st[4 * n + b];
+}
+
 __global__ void __launch_bounds__(LUT_THREADS)
 lut_full_kernel(int n_sets, const double* __restrict__ structure, double* __restrict__ lut)
 {
@@ -249,31 +275,31 @@ lut_full_kernel(int n_sets, const double* __restrict__ structure, double* __rest
     __shared__ double s_pn0[GORT_NTH];
     __shared__ double s_epg[GORT_NTH];
     __shared__ double s_sin2[GORT_NTH];
-    const int m = blockIdx.x;
+    const int m0 = blockIdx.x;
     const int t = threadIdx.x;
+    const size_t N = (size_t) n_sets;
+    // group heads: a set whose crown shape differs from its predecessor's, or that sits on a chunk boundary
+    if (m0 > 0 && (m0 % LUT_GROUP_CAP) != 0 && same_shape(structure, N, m0, m0 - 1)) return;
+    int m1 = m0 + 1;
+    while (m1 < n_sets && (m1 % LUT_GROUP_CAP) != 0 && same_shape(structure, N, m1, m1 - 1)) m1++;
 
-    // ---- gortt_init_params, gortt.c:641-697 --------------------------------------------------
-    const double lambda = structure[0 * (size_t) n_sets + m];
-    const double r      = structure[1 * (size_t) n_sets + m];
-    const double b      = structure[2 * (size_t) n_sets + m];
-    const double h1     = structure[3 * (size_t) n_sets + m];
-    const double h2     = structure[4 * (size_t) n_sets + m];
-    const double favd   = structure[5 * (size_t) n_sets + m];
+    // ---- gortt_init_params, gortt.c:641-697: the shape-only part ------------------------------------
+    const double r      = structure[1 * N + m0];
+    const double b      = structure[2 * N + m0];
+    const double h1     = structure[3 * N + m0];
+    const double h2     = structure[4 * N + m0];
     const double ellip = b / r;
     Crown c;
     c.r = r; c.rr = r * r; c.rrr = c.rr * r;
     const double z1 = h1 - r * ellip;
     const double z2 = h2 + r * ellip;
-    const double lv = lambda / (h2 - h1);
-    const double favd_p = favd * ellip;
-    c.tau_p = 0.5 * favd_p;
-    c.lv_p = lv * ellip;
     c.z2_p = z2 / ellip;
     c.h1_p = h1 / ellip;
     c.h2_p = h2 / ellip;
     const double dz = (double) (z2 - z1) / ((double) GORT_NLAYERS - 1.0);
     c.ds = dz;
     c.dz_p = dz / ellip;
+    c.lv_p = 0.0; c.tau_p = 0.0;                 // per member, below
     if (t < GORT_NLAYERS) {                                                      // gortt.c:778-781
         double height = z2 - dz * (double) (GORT_NLAYERS - 1 - t);
         s_hp[t] = height / ellip;
@@ -281,73 +307,110 @@ lut_full_kernel(int n_sets, const double* __restrict__ structure, double* __rest
     __syncthreads();
 
     const double dth = 1 * GORT_PI / 180.0;
-    double e_t = 0.0, pn0_0 = 0.0, theta = 0.0;
+    double theta = 0.0, es = 0.0;
+    double vg[GORT_NLAYERS];            // v_g[h][t]
+    double s_p[LUT_NSP], tube[LUT_NSP]; // per entry height: path length to the canopy bottom, tube-volume difference
+    Ang a;
+    a.th = a.s = a.c = a.t = 0.0;
     if (t < GORT_NTH) {
         theta = dth * (double) t;                                                // gortt.c:783-797
         if (theta >= GORT_PI / 2.0) theta = GORT_PI / 2.0 - 1.0 * GORT_PI / 180.0;
-        Ang a;
         a.th = atan(tan(theta) * ellip);
         if (a.th >= GORT_PI / 2.0) a.th = GORT_PI / 2.0 - 1.0 * GORT_PI / 180.0;
         a.s = sin(a.th); a.c = cos(a.th); a.t = tan(a.th);
-
-        // ---- P(n=0), gortt_pn_kopen.c:24-32 ---------------------------------------------------
-        double pn0[GORT_NLAYERS];
+        s_sin2[t] = sin(2.0 * theta);
 #pragma unroll 1
-        for (int h = 0; h < GORT_NLAYERS; h++) {
-            double vg = proj_volume(c, a, s_hp[h]);
-            pn0[h] = exp(-1.0 * c.lv_p * vg);
-        }
-        pn0_0 = pn0[0];
-
+        for (int h = 0; h < GORT_NLAYERS; h++) vg[h] = proj_volume(c, a, s_hp[h]);       // gortt_pn_kopen.c:29
         if (t < GORT_NTH - 1) {                                                  // :1099
             const double hp0 = s_hp[0];
-            const double es = expected_single_crown_path(c, a, hp0);             // :445
+            es = expected_single_crown_path(c, a, hp0);                          // :445
 #pragma unroll 1
-            for (int sp_i = GORT_NLAYERS - 2; sp_i > 0; sp_i--) {                // :457 (sp_i = 14 adds p_s0 = 0)
+            for (int k = 0; k < LUT_NSP; k++) {
+                const int sp_i = GORT_NLAYERS - 2 - k;                           // :457, 13 down to 1
                 const double hps = s_hp[sp_i];
-                const double s_p = (double) (hps - hp0) / a.c;                   // :464
-                const double P_s_p = pn0[sp_i + 1] - pn0[sp_i];                  // :43, :482
-                double temp1 = tube_vol(c, a, hp0, hps, c.h2_p) - tube_vol(c, a, hp0, hps, c.h1_p);   // :496
-                temp1 *= c.lv_p;                                                 // :497
-                const double E = exp(-temp1);
-                double pw = 1.0, fact = 1.0;
-#pragma unroll 1
-                for (int n = 1; n <= LUT_MAXCROWNS; n++) {                       // :489
-                    pw *= temp1;                                                 // temp1^n
-                    fact *= (double) n;                                          // gortt.c:752-754
-                    double P_n = (pw * E) / (fact * (1.0 - E));                  // :501-502
-                    double s = s_p * (1.0 - exp(-1.0 * (double) n * es / s_p));  // :508
-                    int idx = (int) (s / c.ds + 0.5);                            // :134-139, :522
-                    // gortt_calc_epgap + gortt_calc_pgap, :1110-1114, :1138
-                    e_t += exp(-((double) idx * c.ds) * c.tau_p) * (P_n * P_s_p);
-                }
+                s_p[k] = (double) (hps - hp0) / a.c;                             // :464
+                tube[k] = tube_vol(c, a, hp0, hps, c.h2_p) - tube_vol(c, a, hp0, hps, c.h1_p);   // :496
             }
         }
-        s_pn0[t] = pn0_0;
-        s_epg[t] = e_t;
-        s_sin2[t] = sin(2.0 * theta);
-        double* o = lut + (size_t) m * GORT_LUT_STRIDE;
-        o[t] = pn0_0;
-        o[GORT_NTH + t] = e_t;
     }
-    __syncthreads();
 
-    // ---- gortt_calc_kopen, gortt_pn_kopen.c:351-375 for h = 0, sequential like the reference ----
-    if (t == 0) {
-        double ko = 0.0, ke = 0.0;
-        double tmp1_last = s_pn0[0] * s_sin2[0];
-        double tmp2_last = s_epg[0] * s_sin2[0];
-        for (int i = 1; i < GORT_NTH; i++) {
-            double tmp1 = s_pn0[i] * s_sin2[i];
-            ko += (tmp1 + tmp1_last) / 2.0 * dth;
-            tmp1_last = tmp1;
-            double tmp2 = s_epg[i] * s_sin2[i];
-            ke += (tmp2 + tmp2_last) / 2.0 * dth;
-            tmp2_last = tmp2;
+    // ---- members of the group -----------------------------------------------------------------------
+    for (int m = m0; m < m1; m++) {
+        const double lambda = structure[0 * N + m];
+        const double favd   = structure[5 * N + m];
+        const double lv = lambda / (h2 - h1);
+        const double favd_p = favd * ellip;
+        const double tau_p = 0.5 * favd_p;
+        const double lv_p = lv * ellip;
+        double e_t = 0.0, pn0_0 = 0.0;
+        if (t < GORT_NTH) {
+            double pn0_hi = exp(-1.0 * lv_p * vg[GORT_NLAYERS - 1]);             // p_n0[14][t]
+            pn0_0 = exp(-1.0 * lv_p * vg[0]);                                    // gortt_pn_kopen.c:30
+            if (t < GORT_NTH - 1) {
+#pragma unroll 1
+                for (int k = 0; k < LUT_NSP; k++) {
+                    const int sp_i = GORT_NLAYERS - 2 - k;
+                    const double pn0_lo = exp(-1.0 * lv_p * vg[sp_i]);
+                    const double P_s_p = pn0_hi - pn0_lo;                        // :43, :482  p_n0[sp_i+1] - p_n0[sp_i]
+                    pn0_hi = pn0_lo;
+                    const double temp1 = tube[k] * lv_p;                         // :497
+                    const double E = exp(-temp1);
+                    const double sp = s_p[k];
+                    // crown-count loop, gortt_pn_kopen.c:489-527, with its loop invariants hoisted:
+                    //   P(n) = temp1^n e^-temp1 / (n! (1 - e^-temp1))             :501-502
+                    //   s    = s' (1 - exp(-n E[S]/s'))                            :508
+                    // exp(-n x) is advanced as q^n (q = exp(-x)); because s selects a histogram bin through
+                    // (int)(s/ds + 0.5) (:134-139, :522) the literal exp is evaluated instead whenever the
+                    // product form lands within 1e-9 of a bin boundary, so the bin is always the one the literal
+                    // formula gives.
+                    const double c0 = E / (1.0 - E);
+                    const double x = es / sp;
+                    const double q = exp(-x);
+                    double pw = 1.0, qn = 1.0;
+                    int last_idx = -1;
+                    double last_w = 0.0;
+#pragma unroll 1
+                    for (int n = 1; n <= LUT_MAXCROWNS; n++) {                   // :489
+                        pw *= temp1;                                             // temp1^n
+                        qn *= q;
+                        const double P_n = pw * c0 * c_inv_fact[n];
+                        double u = sp * (1.0 - qn) / c.ds + 0.5;
+                        if (fabs(u - rint(u)) < 1e-9)
+                            u = sp * (1.0 - exp(-1.0 * (double) n * es / sp)) / c.ds + 0.5;
+                        const int idx = (int) u;
+                        // gortt_calc_epgap + gortt_calc_pgap, :1110-1114, :1138; the bin's attenuation is
+                        // re-used while consecutive crown counts fall into the same bin (s saturates at s')
+                        if (idx != last_idx) { last_w = exp(-((double) idx * c.ds) * tau_p); last_idx = idx; }
+                        e_t += last_w * (P_n * P_s_p);
+                    }
+                }
+            }
+            s_pn0[t] = pn0_0;
+            s_epg[t] = e_t;
+            double* o = lut + (size_t) m * GORT_LUT_STRIDE;
+            o[t] = pn0_0;
+            o[GORT_NTH + t] = e_t;
         }
-        double* o = lut + (size_t) m * GORT_LUT_STRIDE;
-        o[2 * GORT_NTH] = ko;
-        o[2 * GORT_NTH + 1] = ke;
+        __syncthreads();
+
+        // ---- gortt_calc_kopen, gortt_pn_kopen.c:351-375 for h = 0, sequential like the reference ----
+        if (t == 0) {
+            double ko = 0.0, ke = 0.0;
+            double tmp1_last = s_pn0[0] * s_sin2[0];
+            double tmp2_last = s_epg[0] * s_sin2[0];
+            for (int i = 1; i < GORT_NTH; i++) {
+                double tmp1 = s_pn0[i] * s_sin2[i];
+                ko += (tmp1 + tmp1_last) / 2.0 * dth;
+                tmp1_last = tmp1;
+                double tmp2 = s_epg[i] * s_sin2[i];
+                ke += (tmp2 + tmp2_last) / 2.0 * dth;
+                tmp2_last = tmp2;
+            }
+            double* o = lut + (size_t) m * GORT_LUT_STRIDE;
+            o[2 * GORT_NTH] = ko;
+            o[2 * GORT_NTH + 1] = ke;
+        }
+        __syncthreads();
     }
 }
 
@@ -405,6 +468,15 @@ lut_q08_kernel(int n_sets, const double* __restrict__ structure, double* __restr
 
 int launch_lut(gort_ctx *ctx, cudaStream_t s, int n_sets, const double *structure, int method, double *lut)
 {
+    static bool table_ready = false;
+    if (!table_ready) {
+        double h[LUT_MAXCROWNS + 1], f = 1.0;
+        h[0] = 1.0;
+        for (int n = 1; n <= LUT_MAXCROWNS; n++) { f *= (double) n; h[n] = 1.0 / f; }
+        cudaError_t e = cudaMemcpyToSymbol(c_inv_fact, h, sizeof h);
+        if (e != cudaSuccess) return check_cuda(ctx, e, "LUT factorial table");
+        table_ready = true;
+    }
     if (method == GORT_LUT_Q08) lut_q08_kernel<<<n_sets, LUT_THREADS, 0, s>>>(n_sets, structure, lut);
     else lut_full_kernel<<<n_sets, LUT_THREADS, 0, s>>>(n_sets, structure, lut);
     ctx->launches++;

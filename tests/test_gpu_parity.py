@@ -314,3 +314,100 @@ def test_c2_full_size_properties(gort, oracle):
     gort.synchronize()
     ref2 = gort.brdf(st, lut, ang2, rl[0], tl[0], rs[0])
     assert np.array_equal(outp.cpu().numpy()[:, :, :2101], ref2)
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE.json configs 3-5 at FULL size: oracle on a subsample + size-independent properties
+def test_c5_full_grid_properties_and_group_invariance(gort, oracle):
+    """131 072 LUTs.  Consecutive grid points share the crown shape (cover and favd vary fastest), so the kernel
+    computes the shape-only part once per group of sets; a set must get the same BITS whether it is computed
+    inside a group, at a chunk boundary, or alone (this is also what makes the result independent of how the
+    grid is sharded over GPUs)."""
+    st = wk.c5_lut_grid()["structure"]
+    M = st.shape[1]
+    lut = gort.lut(st)
+    assert lut.shape == (M, gort_b200.LUT_STRIDE)
+    nan_sets = np.isnan(lut).any(axis=1)
+    ok = ~nan_sets
+    pn0, epg = lut[ok, :91], lut[ok, 91:182]
+    assert np.all((pn0 >= 0) & (pn0 <= 1)) and np.all(epg >= -1e-15) and np.all(epg[:, 90] == 0.0)
+    assert np.all(np.diff(pn0[:, :90], axis=1) <= 1e-12)            # gap probability falls with zenith
+    assert np.all(lut[ok, 182] >= 0) and np.all(lut[ok, 182] <= 1.01)      # trapezoid of p_n0 sin(2 theta) over the clamped theta grid
+    # same bits alone, in a different batch composition, and across chunk boundaries
+    rng = np.random.Generator(np.random.PCG64(5))
+    pick = np.unique(np.concatenate([rng.integers(0, M, 40), [0, 63, 64, 65, 127, 128, M - 1]]))
+    for k in pick:
+        alone = gort.lut(np.ascontiguousarray(st[:, k:k + 1]))[0]
+        assert np.array_equal(alone, lut[k], equal_nan=True), "set %d differs when computed alone" % k
+    lo = 777
+    part = gort.lut(np.ascontiguousarray(st[:, lo:lo + 500]))
+    assert np.array_equal(part, lut[lo:lo + 500], equal_nan=True)
+    # NaN sets: the reference yields NaN for the same sets and entries (oracle on a sample of them + neighbours)
+    idx = np.flatnonzero(nan_sets)
+    print("C5: %d of %d LUTs contain NaN" % (idx.size, M))
+    for k in np.concatenate([idx[:: max(1, idx.size // 6)][:6], idx[:1] - 1 if idx.size and idx[0] > 0 else []]).astype(int):
+        lo_ = oracle.lut(st[:, k])
+        sens = sensitivity(lambda c: c.lut(st[:, k]), lo_)
+        assert_close_cond(lut[k], lo_, sens, "C5 grid point %d %r" % (k, st[:, k]))
+
+
+def test_c4_full_size(gort, oracle):
+    """10^5 members x 16 geometries x 7 bands, everything varying (LUT + spectra + BRDF on the GPU)."""
+    w = wk.c4_enkf()
+    st, ang, wl = w["structure"], w["angles"], w["wavelength"]
+    M = st.shape[1]
+    lut = gort.lut(st)
+    rl, tl, rs = gort.spectra(w["leaf"], w["soil"], wl)
+    rsurf = gort.brdf(st, lut, ang, rl, tl, rs)
+    assert rsurf.shape == (M, 16, 7)
+    bad_lut = np.isnan(lut).any(axis=1)
+    # non-finite reflectances are part of the reference's behaviour (a zero within-crown gap probability in the
+    # interpolated LUT row gives -log(0) in the hotspot, SURVEY.md App. B6): they must be rare and must coincide
+    # with the reference's, which the sampled comparison below checks on some of them explicitly
+    nonfin = ~np.isfinite(rsurf).all(axis=(1, 2))
+    assert nonfin.mean() < 0.01
+    fin = rsurf[~nonfin]
+    assert fin.min() >= 0.0 and fin.max() < 1.5
+    worst = 0.0
+    sample = list(range(0, M, 4001)) + list(np.flatnonzero(nonfin & ~bad_lut)[:4]) + list(np.flatnonzero(bad_lut)[:2])
+    for m in sample:
+        lut_o = oracle.lut(st[:, m])
+        sens = sensitivity(lambda c: c.lut(st[:, m]), lut_o)
+        assert_close_cond(lut[m], lut_o, sens, "C4 LUT member %d" % m)
+        sp = oracle.spectra(w["leaf"][:, m], w["soil"][:, m], wl)
+        r_o, _, _ = oracle.brdf(st[:, m], lut[m], ang[:, m, :].T, *sp)      # same LUT: isolates the BRDF path
+        worst = max(worst, assert_close(rsurf[m], r_o, "C4 member %d" % m))
+    print("C4 full size: worst rel err %.3e over %d sampled members, %d members with NaN LUT, %d with non-finite output" % (
+        worst, len(sample), bad_lut.sum(), nonfin.sum()))
+    # 4a: structure shared, LAI only varying -> every member shares the crown shape (one LUT group per 64 members)
+    wa = wk.c4_enkf(n_members=1000, vary_structure=False)
+    luta = gort.lut(wa["structure"])
+    for m in (0, 63, 64, 500, 999):
+        assert np.array_equal(gort.lut(np.ascontiguousarray(wa["structure"][:, m:m + 1]))[0], luta[m], equal_nan=True)
+        assert_close(luta[m], oracle.lut(wa["structure"][:, m]), "C4a LUT member %d" % m)
+
+
+def test_c3_full_size(gort, oracle):
+    """10^4 parameter sets x 3 sun angles x 211 bands x 512 quadrature nodes."""
+    w = wk.c3_albedo()
+    st, ang, wl = w["structure"], w["angles"], w["wavelength"]
+    M = st.shape[1]
+    lut = gort.lut(st)
+    rl, tl, rs = gort.spectra(w["leaf"], w["soil"], wl)
+    alb, fv, fs = gort.energy(st, lut, ang, rl, tl, rs)
+    assert alb.shape == (M, 3, 211)
+    # non-finite results are part of the reference's behaviour (zero within-crown gap probability in a LUT row
+    # -> -log(0) in the hotspot): rare, and compared against the oracle on some of them below
+    good = np.isfinite(alb).all(axis=(1, 2)) & np.isfinite(fv).all(axis=(1, 2)) & np.isfinite(fs).all(axis=(1, 2))
+    assert good.mean() > 0.99
+    a, v, s = alb[good], fv[good], fs[good]
+    assert a.min() > 0.0 and a.max() < 1.0
+    # energy balance: favegt = 1 - albedo - Fd2 + Fu2, fasoil = Fd2 - Fu2  (gortt_albedo.c:48-52)
+    assert np.max(np.abs(a + v + s - 1.0)) < 1e-12
+    print("C3 full size: %d of %d sets with non-finite results" % ((~good).sum(), M))
+    for m in list(range(0, M, 1777)) + list(np.flatnonzero(~good)[:3]):
+        sp = oracle.spectra(w["leaf"][:, m], w["soil"][:, m], wl)
+        a_o, v_o, s_o = oracle.energy(st[:, m], lut[m], ang.T, *sp)
+        assert_close(alb[m], a_o, "C3 albedo set %d" % m)
+        assert_close(fv[m], v_o, "C3 favegt set %d" % m, rtol=1e-8)
+        assert_close(fs[m], s_o, "C3 fasoil set %d" % m)
