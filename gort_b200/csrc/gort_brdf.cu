@@ -399,13 +399,22 @@ int launch_brdf(gort_ctx *ctx, cudaStream_t s, const gort_shape &sh, const doubl
 }
 
 // ------------------------------------------------------------------------------------------------
-// Energy balance.  One CTA of 512 threads per (set, sun line).
-//   phase 1: thread n -> quadrature node (azimuth i = n % 32, zenith j = 16 + n / 32): geometry record
-//   phase 2: per wavelength chunk, threads compute the (sun, lambda) terms into shared memory
-//   phase 3: warp per wavelength, lane = azimuth node, 16 zenith nodes accumulated in the
-//            reference's order (gortt_albedo.c:101-130), azimuth sum by warp shuffle (:132-133)
+// Energy balance (gortt_energy / gortt_albedo, gortt_albedo.c:7-138).  One CTA of 512 threads per (set, sun line).
+//
+// The reference evaluates gortt_rsurf at 32 x 16 Gauss-Legendre nodes of the view hemisphere for every
+// wavelength and sums rsurf * weights (:89-136): 512 x W evaluations per sun angle.  All nodes share the sun, so
+// in the regrouped form of the view loop (gort_rsurf_wide.cuh)
+//        rsurf(node, lambda) = cA(node) A(l) + Kc(node) PDF(l) + cG(node) G(l) + cZ(node) Z(l) + Kt(node) T(l)
+// the five (sun, lambda) terms are common to all nodes and the quadrature is LINEAR in the node coefficients:
+//        albedo(l) = [S cA] A(l) + [S Kc] PDF(l) + [S cG] G(l) + [S cZ] Z(l) + [S Kt] T(l),   S = sum over nodes
+//                                                                                  with weight w_i w_j |mu_j|.
+//   phase 1: thread n -> quadrature node (azimuth i = n % 32, zenith j = 16 + n / 32): its geometry record,
+//            weighted; the five weighted coefficient sums by warp shuffle + a fixed shared-memory tree;
+//   phase 2: thread per wavelength: the (set, lambda) and (sun, lambda) terms once, 5 FMAs, and the energy
+//            balance of gortt_albedo.c:37-52.
+// Work per (set, sun) drops from 512 x W view evaluations to 512 geometry records + W spectral evaluations; the
+// sum runs in a different order than the reference's nested loops (differences ~1e-16 relative).
 #define GORT_EN_THREADS 512
-#define GORT_EN_CHUNK 256
 
 __global__ void __launch_bounds__(GORT_EN_THREADS)
 energy_kernel(int n_sets, int n_geom, int n_wl, int geom_per_set, int spectra_per_set, gort_options opt,
@@ -415,9 +424,9 @@ energy_kernel(int n_sets, int n_geom, int n_wl, int geom_per_set, int spectra_pe
               const double* __restrict__ rsoil,
               double* __restrict__ albedo, double* __restrict__ favegt, double* __restrict__ fasoil)
 {
-    __shared__ double nrec[7][GORT_EN_THREADS];         // Kc Kg Kt Kz Kpg Kpz q per node
+    __shared__ double part[5][GORT_EN_THREADS / 32];    // per-warp partial sums of the weighted coefficients
+    __shared__ double coef[5];
     __shared__ double sunv[6];                          // fd mus t0 tp0 pe_s pn0_s
-    __shared__ double lam[6][GORT_EN_CHUNK];            // A PD FCf G Z T per wavelength of the chunk
     __shared__ double s_absc[GORT_NQUAD], s_wts[GORT_NQUAD];
 
     const long L = (long) n_sets * n_geom;
@@ -443,57 +452,40 @@ energy_kernel(int n_sets, int n_geom, int n_wl, int geom_per_set, int spectra_pe
         double x = xm + xr * s_absc[j];                                          // :103
         double vza = acos(x);                                                    // :105
         GeomRec r = geom_record(c, lut + (size_t) m * GORT_LUT_STRIDE, opt, vza, g.sza, raa, fd);
-        nrec[0][tid] = r.Kc; nrec[1][tid] = r.Kg; nrec[2][tid] = r.Kt; nrec[3][tid] = r.Kz;
-        nrec[4][tid] = r.Kpg; nrec[5][tid] = r.Kpz; nrec[6][tid] = r.q;
+        const double wn = (s_wts[j] * fabs(x) * xr) * (s_wts[i] * yr);           // :128-129, :132-133
+        double v[5] = {wn * r.cA, wn * r.Kc, wn * r.cG, wn * r.cZ, wn * r.Kt};
+#pragma unroll
+        for (int k = 0; k < 5; k++) {
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], off);
+            if ((tid & 31) == 0) part[k][tid >> 5] = v[k];
+        }
         if (tid == 0) {
             sunv[0] = r.fd; sunv[1] = r.mus; sunv[2] = r.t0; sunv[3] = r.tp0; sunv[4] = r.pe_s; sunv[5] = r.pn0_s;
         }
     }
     __syncthreads();
+    if (tid < 5) {
+        double sum = 0.0;
+        for (int w = 0; w < GORT_EN_THREADS / 32; w++) sum += part[tid][w];
+        coef[tid] = sum;
+    }
+    __syncthreads();
     const double mus = sunv[1], t0 = sunv[2], tp0 = sunv[3], pe = sunv[4], Pn0 = sunv[5];
+    const double CA = coef[0], CP = coef[1], CG = coef[2], CZ = coef[3], CT = coef[4];
     const size_t sb = spectra_per_set ? (size_t) m * n_wl : 0;
-    const int lane = tid & 31, warp = tid >> 5;
-
-    for (int wbase = 0; wbase < n_wl; wbase += GORT_EN_CHUNK) {
-        const int nc = min(GORT_EN_CHUNK, n_wl - wbase);
-        __syncthreads();
-        if (tid < nc) {
-            const int w = wbase + tid;
-            LeafTerms Lf = leaf_terms(c, rleaf[sb + w], tleaf[sb + w], rsoil[sb + w]);
-            SunTerms S = sun_terms(c, Lf, fd, mus, t0, tp0, pe);
-            lam[0][tid] = Lf.A; lam[1][tid] = S.PD; lam[2][tid] = S.FCf;
-            lam[3][tid] = S.G; lam[4][tid] = S.Z; lam[5][tid] = S.T;
-        }
-        __syncthreads();
-        for (int k = warp; k < nc; k += GORT_EN_THREADS / 32) {
-            LeafTerms Lf; SunTerms S;
-            Lf.A = lam[0][k]; S.PD = lam[1][k]; S.FCf = lam[2][k]; S.G = lam[3][k]; S.Z = lam[4][k]; S.T = lam[5][k];
-            double sum_x = 0.;
-#pragma unroll 4
-            for (int jj = 0; jj < GORT_NQUAD / 2; jj++) {
-                const int n = jj * 32 + lane;
-                double C;
-                double r = view_rsurf(c, Lf, S, fd, nrec[6][n], nrec[0][n], nrec[1][n], nrec[2][n], nrec[3][n],
-                                      nrec[4][n], nrec[5][n], C);
-                const int j = GORT_NQUAD / 2 + jj;
-                double x = xm + xr * s_absc[j];
-                sum_x = sum_x + r * s_wts[j] * fabs(x) * xr;                     // :128-129
-            }
-            double v = sum_x * s_wts[lane] * yr;                                 // :132-133
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-            if (lane == 0) {
-                const int w = wbase + k;
-                const size_t o = (size_t) line * n_wl + w;
-                double alb = v / GORT_PI;                                        // :136
-                double rs = rsoil[sb + w];
-                double Fu2 = S.G * Pn0 + S.Z * (1. - Pn0);                       // gortt_albedo.c:48
-                double Fd2 = Pn0 + S.Z * (1. - Pn0) / rs;                        // :49
-                albedo[o] = alb;
-                favegt[o] = 1. - alb - Fd2 + Fu2;                                // :51
-                fasoil[o] = Fd2 - Fu2;                                           // :52
-            }
-        }
+    for (int w = tid; w < n_wl; w += GORT_EN_THREADS) {
+        const double rs = rsoil[sb + w];
+        const LeafTerms Lf = leaf_terms(c, rleaf[sb + w], tleaf[sb + w], rs);
+        const SunTerms S = sun_terms(c, Lf, fd, mus, t0, tp0, pe);
+        const double sum_y = fma(CA, Lf.A, fma(CP, S.PDF, fma(CG, S.G, fma(CZ, S.Z, CT * S.T))));
+        const size_t o = (size_t) line * n_wl + w;
+        const double alb = sum_y / GORT_PI;                                      // :136
+        const double Fu2 = S.G * Pn0 + S.Z * (1. - Pn0);                         // gortt_albedo.c:48
+        const double Fd2 = Pn0 + S.Z * (1. - Pn0) / rs;                          // :49
+        albedo[o] = alb;
+        favegt[o] = 1. - alb - Fd2 + Fu2;                                        // :51
+        fasoil[o] = Fd2 - Fu2;                                                   // :52
     }
 }
 
