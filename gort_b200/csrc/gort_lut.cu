@@ -361,9 +361,10 @@ lut_full_kernel(int n_sets, const double* __restrict__ structure, double* __rest
                     //   s    = s' (1 - exp(-n E[S]/s'))                            :508
                     // exp(-n x) is advanced as q^n (q = exp(-x)); because s selects a histogram bin through
                     // (int)(s/ds + 0.5) (:134-139, :522) the literal exp is evaluated instead whenever the
-                    // product form lands within 1e-9 of a bin boundary, so the bin is always the one the literal
-                    // formula gives.
+                    // product form (with s/ds as s * (1/ds)) lands within 1e-9 of a bin boundary, so the bin is
+                    // always the one the literal formula gives.
                     const double c0 = E / (1.0 - E);
+                    const double inv_ds = 1.0 / c.ds;
                     const double x = es / sp;
                     const double q = exp(-x);
                     double pw = 1.0, qn = 1.0;
@@ -374,7 +375,7 @@ lut_full_kernel(int n_sets, const double* __restrict__ structure, double* __rest
                         pw *= temp1;                                             // temp1^n
                         qn *= q;
                         const double P_n = pw * c0 * c_inv_fact[n];
-                        double u = sp * (1.0 - qn) / c.ds + 0.5;
+                        double u = sp * (1.0 - qn) * inv_ds + 0.5;
                         if (fabs(u - rint(u)) < 1e-9)
                             u = sp * (1.0 - exp(-1.0 * (double) n * es / sp)) / c.ds + 0.5;
                         const int idx = (int) u;
@@ -393,22 +394,25 @@ lut_full_kernel(int n_sets, const double* __restrict__ structure, double* __rest
         }
         __syncthreads();
 
-        // ---- gortt_calc_kopen, gortt_pn_kopen.c:351-375 for h = 0, sequential like the reference ----
-        if (t == 0) {
+        // ---- gortt_calc_kopen, gortt_pn_kopen.c:351-375 for h = 0: the trapezoid panels
+        //      (f_i + f_{i-1})/2 * dth, i = 1..90, summed by warp 0 (three panels per lane, then a shuffle tree;
+        //      the reference adds them left to right -- same panels, different association) ----
+        if (t < 32) {
             double ko = 0.0, ke = 0.0;
-            double tmp1_last = s_pn0[0] * s_sin2[0];
-            double tmp2_last = s_epg[0] * s_sin2[0];
-            for (int i = 1; i < GORT_NTH; i++) {
-                double tmp1 = s_pn0[i] * s_sin2[i];
-                ko += (tmp1 + tmp1_last) / 2.0 * dth;
-                tmp1_last = tmp1;
-                double tmp2 = s_epg[i] * s_sin2[i];
-                ke += (tmp2 + tmp2_last) / 2.0 * dth;
-                tmp2_last = tmp2;
+            for (int i = 1 + t; i < GORT_NTH; i += 32) {
+                ko += (s_pn0[i] * s_sin2[i] + s_pn0[i - 1] * s_sin2[i - 1]) / 2.0 * dth;
+                ke += (s_epg[i] * s_sin2[i] + s_epg[i - 1] * s_sin2[i - 1]) / 2.0 * dth;
             }
-            double* o = lut + (size_t) m * GORT_LUT_STRIDE;
-            o[2 * GORT_NTH] = ko;
-            o[2 * GORT_NTH + 1] = ke;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                ko += __shfl_xor_sync(0xffffffffu, ko, off);
+                ke += __shfl_xor_sync(0xffffffffu, ke, off);
+            }
+            if (t == 0) {
+                double* o = lut + (size_t) m * GORT_LUT_STRIDE;
+                o[2 * GORT_NTH] = ko;
+                o[2 * GORT_NTH + 1] = ke;
+            }
         }
         __syncthreads();
     }
