@@ -23,6 +23,12 @@
  *     The reference convention (print to stderr, exit(EXIT_FAILURE)) is kept by the gortt CLI,
  *     not by the library.
  *   - There is no CPU fallback: without a CUDA device gort_create() fails.
+ *   - One CUDA stream per context at a time.  Consecutive gort_brdf_batch_dev calls of the same shape into the
+ *     same output buffers overlap on the GPU (the geometry kernel of call i+1 runs under the store phase of call
+ *     i; the stores of call i+1 to a region start only after call i's stores to that region are complete), so
+ *     their results are exactly those of running them one after the other.  The overlap is used only when no
+ *     input of call i+1 lies inside an output buffer of call i; any other operation put on the stream between two
+ *     calls (a copy, another kernel) orders them completely, as does switching streams.
  */
 #ifndef GORT_B200_H
 #define GORT_B200_H
