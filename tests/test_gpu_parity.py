@@ -411,3 +411,76 @@ def test_c3_full_size(gort, oracle):
         assert_close(alb[m], a_o, "C3 albedo set %d" % m)
         assert_close(fv[m], v_o, "C3 favegt set %d" % m, rtol=1e-8)
         assert_close(fs[m], s_o, "C3 fasoil set %d" % m)
+
+
+# ---------------------------------------------------------------------------------------------
+# Shapes that exercise the per-wavelength kernel's control flow: several record stages per CTA, runs that cross
+# stage and CTA boundaries, parameter-set changes inside a CTA's line range, every chunking of the spectrum.
+@pytest.mark.parametrize("nw,pitch", [(64, 0), (65, 80), (96, 96), (127, 128), (333, 336), (700, 704), (1153, 1168), (2101, 0)])
+def test_wide_kernel_shapes_partition_invariance(gort, oracle, nw, pitch):
+    import torch
+    rng = np.random.Generator(np.random.PCG64(100 + nw))
+    M = 3
+    G = 16000 if nw <= 128 else (4000 if nw < 1000 else 1500)      # M*G lines: up to ~160 lines per CTA -> 2 stages
+    st = wk.random_structures(rng, M)
+    leaf = wk.random_leaves(rng, M)
+    wl = np.sort(rng.uniform(400, 2500, nw))
+    # runs of random length (1..300 lines) sharing the sun, random views
+    sza = np.empty(G); saa = np.empty(G)
+    k = 0
+    while k < G:
+        n = int(rng.integers(1, 300))
+        sza[k:k + n] = rng.uniform(0, 80); saa[k:k + n] = rng.uniform(0, 360)
+        k += n
+    ang = np.stack([rng.uniform(0, 85, G), rng.uniform(0, 360, G), sza, saa])
+    lut = gort.lut(st)
+    rl, tl, rs = gort.spectra(leaf, np.repeat(wk.DEFAULT_SOIL.reshape(4, 1), M, axis=1), wl)
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    P = pitch if pitch else nw
+    out = torch.full((M, G, P), -3.0, dtype=torch.float64, device=dev)
+    gort.brdf_dev(t(st), t(lut), t(ang), t(rl), t(tl), t(rs), out)
+    gort.synchronize()
+    full = out.cpu().numpy()
+    # columns beyond the padded line are untouched; padding inside the last 128-byte line copies the last band
+    ncol = min(P, (nw + 15) // 16 * 16) if P % 16 == 0 else nw
+    assert np.all(full[:, :, ncol:] == -3.0)
+    if ncol > nw:
+        assert np.array_equal(full[:, :, nw:ncol], np.repeat(full[:, :, nw - 1:nw], ncol - nw, axis=2))
+    full = full[:, :, :nw]
+    # same bits when the lines are evaluated in separate calls, one set at a time, cut at arbitrary places
+    cuts = [0, 1, 130, 131, 5000 if G > 5000 else G // 2, G]
+    for m in range(M):
+        for lo, hi in zip(cuts[:-1], cuts[1:]):
+            part = gort.brdf(st[:, m:m + 1], lut[m:m + 1], ang[:, lo:hi], rl[m], tl[m], rs[m])
+            assert np.array_equal(part[0], full[m, lo:hi], equal_nan=True), "set %d lines %d:%d differ from the batched call" % (m, lo, hi)
+    # oracle on a subsample of lines of every set
+    idx = np.unique(np.concatenate([np.arange(0, G, max(1, G // 25)), [0, 127, 128, 129, G - 1]]))
+    for m in range(M):
+        lut_o = oracle.lut(st[:, m])
+        r_o, _, _ = oracle.brdf(st[:, m], lut[m], ang[:, idx].T, rl[m], tl[m], rs[m])
+        assert_close(full[m, idx], r_o, "set %d" % m)
+    # component signatures through the scomp variant of the kernel: rsurf must agree with the fast path to rounding
+    r2, sc = gort.brdf(st, lut, ang[:, :600], rl, tl, rs, want_scomp=True)
+    assert_close(r2, full[:, :600], "scomp-path rsurf vs fast path", rtol=1e-12)
+    for m in range(M):
+        _, s_o, _ = oracle.brdf(st[:, m], lut[m], ang[:, :40].T, rl[m], tl[m], rs[m])
+        assert_close(sc[m, :40], s_o, "scomp set %d" % m)
+
+
+def test_small_and_degenerate_shapes(gort, oracle):
+    """one line, one band, one set; band-set kernel boundary at W = 63 / 64."""
+    st = gort_b200.structure_from_options(lai=2.5).reshape(6, 1)
+    lut = gort.lut(st)
+    for nw in (1, 2, 63, 64):
+        wl = np.linspace(400.0, 2500.0, nw)
+        rl, tl, rs = gort.spectra(wk.DEFAULT_LEAF.reshape(7, 1), wk.DEFAULT_SOIL.reshape(4, 1), wl)
+        for ang in (np.array([[12.0], [40.0], [33.0], [250.0]]), np.array([[0.0, 60.0], [0.0, 10.0], [0.0, 60.0], [0.0, 10.0]])):
+            r = gort.brdf(st, lut, ang, rl[0], tl[0], rs[0])
+            r_o, _, _ = oracle.brdf(st[:, 0], lut[0], ang.T, rl[0], tl[0], rs[0])
+            assert_close(r[0], r_o, "nw %d" % nw)
+            a, v, s = gort.energy(st, lut, ang, rl[0], tl[0], rs[0])
+            a_o, v_o, s_o = oracle.energy(st[:, 0], lut[0], ang.T, rl[0], tl[0], rs[0])
+            assert_close(a[0], a_o, "albedo nw %d" % nw); assert_close(v[0], v_o, "favegt", rtol=1e-8); assert_close(s[0], s_o, "fasoil")
+    with pytest.raises(gort_b200.GortError):
+        gort.brdf(st, lut, np.zeros((4, 0)), np.zeros(3), np.zeros(3), np.zeros(3))
