@@ -126,10 +126,25 @@ const char *gort_last_error(const gort_ctx *ctx) { return ctx ? ctx->err : g_cre
 void *gort_stream(gort_ctx *ctx) { return ctx ? (void *) ctx->stream : NULL; }
 long gort_launch_count(const gort_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
+// the BRDF pipeline's in-kernel waits are bounded; one that expired (a broken predecessor) leaves a mark
+static int check_pipeline_fault(gort_ctx *ctx)
+{
+    if (!ctx->d_done) return GORT_OK;
+    unsigned long long f = 0;
+    cudaError_t e = cudaMemcpy(&f, ctx->d_done + GORT_MAX_WIDE_CTAS, sizeof f, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return check_cuda(ctx, e, "pipeline fault word");
+    if (f) return set_error(ctx, GORT_ERR_CUDA, "BRDF pipeline: an in-kernel wait timed out in call %llu; results of that call are not ordered", f);
+    return GORT_OK;
+}
+
 int gort_synchronize(gort_ctx *ctx)
 {
     if (!ctx) return GORT_ERR_INVALID;
-    return check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "synchronize");
+    TRYCUDA(ctx, cudaSetDevice(ctx->device), "cudaSetDevice");
+    // everything this context enqueued, on its own stream and on the last caller-supplied one
+    TRYCUDA(ctx, cudaStreamSynchronize(ctx->stream), "synchronize");
+    if (ctx->last_stream && ctx->last_stream != ctx->stream) TRYCUDA(ctx, cudaStreamSynchronize(ctx->last_stream), "synchronize");
+    return check_pipeline_fault(ctx);
 }
 
 void *gort_host_alloc(size_t bytes)
@@ -313,7 +328,8 @@ int gort_brdf_batch(gort_ctx *ctx, const gort_shape *shape, const double *struct
     TRY(d2h(ctx, rsurf, d_rsurf, nl * hp));
     TRY(d2h(ctx, scomp, d_scomp, 4 * nl * hp));
     TRY(d2h(ctx, kprop, d_kprop, 4 * nl));
-    return check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "gort_brdf_batch");
+    TRY(check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "gort_brdf_batch"));
+    return check_pipeline_fault(ctx);
 }
 
 int gort_energy_batch_dev(gort_ctx *ctx, void *stream, const gort_shape *shape, const double *structure,

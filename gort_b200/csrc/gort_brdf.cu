@@ -174,7 +174,7 @@ static int launch_wide(gort_ctx *ctx, cudaStream_t s, const gort_shape &sh, long
     a.pitch = sh.out_pitch > 0 ? sh.out_pitch : sh.n_wl;
     a.structure = structure; a.lut = lut; a.rec = rec; a.rleaf = rleaf; a.tleaf = tleaf; a.rsoil = rsoil;
     a.rsurf = rsurf; a.scomp = scomp;
-    a.done = ctx->d_done;
+    a.done = ctx->d_done; a.fault = ctx->d_done + GORT_MAX_WIDE_CTAS;
     a.tile_flags = ctx->d_tile_flags; a.call_no = ctx->call_no;
     a.tl = timeline_buffer();                                           // consecutive calls stamp alternate halves (set below)
     const size_t smem = sizeof(double2) * 8 * WIDE_STAGE_LINES + sizeof(unsigned) * (WIDE_STAGE_LINES / 32)
@@ -280,9 +280,9 @@ int launch_brdf(gort_ctx *ctx, cudaStream_t s, const gort_shape &sh, const doubl
     static int use_pdl = getenv("GORT_NO_PDL") ? 0 : 1;
     static int use_xcall = getenv("GORT_NO_XCALL") ? 0 : 1;
     if (!ctx->d_done) {
-        if (cudaMalloc((void **) &ctx->d_done, sizeof(unsigned long long) * GORT_MAX_WIDE_CTAS) != cudaSuccess)
+        if (cudaMalloc((void **) &ctx->d_done, sizeof(unsigned long long) * (GORT_MAX_WIDE_CTAS + 1)) != cudaSuccess)
             return set_error(ctx, GORT_ERR_NOMEM, "cudaMalloc of the pipeline flags failed");
-        cudaMemset(ctx->d_done, 0, sizeof(unsigned long long) * GORT_MAX_WIDE_CTAS);
+        cudaMemset(ctx->d_done, 0, sizeof(unsigned long long) * (GORT_MAX_WIDE_CTAS + 1));
         cudaEventCreateWithFlags(&ctx->xstream_ev, cudaEventDisableTiming);
     }
     // calls on different streams are ordered one after the other (record buffers and the counter are shared)
@@ -408,18 +408,80 @@ int launch_brdf(gort_ctx *ctx, cudaStream_t s, const gort_shape &sh, const doubl
 // the five (sun, lambda) terms are common to all nodes and the quadrature is LINEAR in the node coefficients:
 //        albedo(l) = [S cA] A(l) + [S Kc] PDF(l) + [S cG] G(l) + [S cZ] Z(l) + [S Kt] T(l),   S = sum over nodes
 //                                                                                  with weight w_i w_j |mu_j|.
-//   phase 1: thread n -> quadrature node (azimuth i = n % 32, zenith j = 16 + n / 32): its geometry record,
-//            weighted; the five weighted coefficient sums by warp shuffle + a fixed shared-memory tree;
-//   phase 2: thread per wavelength: the (set, lambda) and (sun, lambda) terms once, 5 FMAs, and the energy
-//            balance of gortt_albedo.c:37-52.
-// Work per (set, sun) drops from 512 x W view evaluations to 512 geometry records + W spectral evaluations; the
-// sum runs in a different order than the reference's nested loops (differences ~1e-16 relative).
+// Two kernels:
+//   energy_zenith_kernel  one thread per (sun line, view-zenith node): everything of the geometry record that does
+//                         not depend on the azimuth -- primed trig of both zeniths, the raa = 0 and raa = pi passes
+//                         of gortt_kc, the crown terms, the exp terms, beta, LUT interpolation, the zenith part of
+//                         the hotspot.  The reference recomputes all of it at each of the 32 azimuth nodes.
+//   energy_kernel         one CTA of 512 threads per (set, sun line): thread n -> node (azimuth i = n % 32,
+//                         zenith j = 16 + n / 32): the pass at its own relative azimuth and the pair part of the
+//                         hotspot, the weighted coefficients, their sums by warp shuffle + a fixed shared-memory
+//                         tree; then one thread per wavelength: the (set, lambda) and (sun, lambda) terms once,
+//                         5 FMAs, and the energy balance of gortt_albedo.c:37-52.
+// Work per (set, sun) drops from 512 x W view evaluations + 512 full geometry records to 16 zenith records +
+// 512 azimuth passes + W spectral evaluations; the sums run in a different order than the reference's nested
+// loops (differences ~1e-16 relative).
 #define GORT_EN_THREADS 512
+#define GORT_EN_NZ (GORT_NQUAD / 2)       // view-zenith nodes (mu > 0)
+#define GORT_EN_ZREC 32                   // doubles per zenith record
+
+// zenith record layout (doubles)
+enum { ZR_VZA = 0, ZR_VZA_P, ZR_SZA_P, ZR_TS, ZR_TV, ZR_SECS, ZR_SECV, ZR_CS, ZR_CV, ZR_SS, ZR_SV,
+       ZR_MV, ZR_THETA_MI, ZR_GAMMA_V, ZR_F0F0, ZR_F180F180, ZR_EV, ZR_ES, ZR_T0, ZR_BETA,
+       ZR_PN0S, ZR_PES, ZR_PEV, ZR_SSZ, ZR_CSZ, ZR_SVZ, ZR_CVZ, ZR_LSZA, ZR_LVZA, ZR_FD, ZR_X, ZR_END };
+static_assert(ZR_END <= GORT_EN_ZREC, "zenith record too small");
+
+__global__ void __launch_bounds__(128)
+energy_zenith_kernel(int n_sets, int n_geom, int geom_per_set, gort_options opt,
+                     const double* __restrict__ structure, const double* __restrict__ lut,
+                     const double* __restrict__ angles, const double* __restrict__ gl, double* __restrict__ zrec)
+{
+    const long L = (long) n_sets * n_geom;
+    const long item = (long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (item >= L * GORT_EN_NZ) return;
+    const long line = item / GORT_EN_NZ;
+    const int jj = (int) (item - line * GORT_EN_NZ);
+    const int m = (int) (line / n_geom);
+    const long a = geom_per_set ? line : (line - (long) m * n_geom);
+    const long na = geom_per_set ? L : n_geom;
+    const Canopy c = canopy_load(structure, n_sets, m, lut);
+    const double* lut_m = lut + (size_t) m * GORT_LUT_STRIDE;
+    const Line g = line_from_degrees(angles[0 * na + a], angles[1 * na + a], angles[2 * na + a], angles[3 * na + a]);
+    const double xr = 0.5 * (1. + 1.), xm = 0.5 * (1. - 1.);                     // gortt_albedo.c:82-83
+    const double x = xm + xr * gl[GORT_NQUAD / 2 + jj];                          // :103
+    const double vza = acos(x);                                                  // :105
+    const double fd = opt.use_fd ? opt.fd : cos(g.sza) / (cos(g.sza) + 0.09);    // gortt.c:290-291
+    const Primed P = primed_trig(c, vza, g.sza);
+    const CrownLite s = crown_lite(c, P.t);
+    const bool vgs = fabs(vza) > fabs(g.sza);
+    const Pass a0 = kc_pass(c, P, s, vgs, 0.0, 1.0, 0.0);                        // gortt_brdf.c:143-146
+    const Pass a180 = kc_pass(c, P, s, vgs, GORT_PI, -1.0, GORT_SIN_PI);         // :147-150
+    const Tail tl = tail_terms(c, P, opt);
+    double pn0_s, pe_s, pn0_v, pe_v;
+    zenith_lerp(lut_m, g.sza, pn0_s, pe_s);                                      // gortt.c:872-915
+    zenith_lerp(lut_m, vza, pn0_v, pe_v);
+    double ssz, csz, svz, cvz;
+    sincos(g.sza, &ssz, &csz);
+    sincos(vza, &svz, &cvz);
+    double* z = zrec + (size_t) item * GORT_EN_ZREC;
+    z[ZR_VZA] = vza; z[ZR_VZA_P] = P.vza_p; z[ZR_SZA_P] = P.sza_p;
+    z[ZR_TS] = P.t.ts; z[ZR_TV] = P.t.tv; z[ZR_SECS] = P.t.secs; z[ZR_SECV] = P.t.secv;
+    z[ZR_CS] = P.t.cs; z[ZR_CV] = P.t.cv; z[ZR_SS] = P.t.ss; z[ZR_SV] = P.t.sv;
+    z[ZR_MV] = s.Mv; z[ZR_THETA_MI] = s.theta_Mi; z[ZR_GAMMA_V] = s.Gamma_v;
+    z[ZR_F0F0] = a0.f * a0.F; z[ZR_F180F180] = a180.f * a180.F;
+    z[ZR_EV] = tl.e_v; z[ZR_ES] = tl.e_s; z[ZR_T0] = tl.t0; z[ZR_BETA] = tl.beta;
+    z[ZR_PN0S] = pn0_s; z[ZR_PES] = pe_s; z[ZR_PEV] = pe_v;
+    z[ZR_SSZ] = ssz; z[ZR_CSZ] = csz; z[ZR_SVZ] = svz; z[ZR_CVZ] = cvz;
+    z[ZR_LSZA] = -log(pe_s) / c.kfavd;                                           // gortt_brdf.c:659-660
+    z[ZR_LVZA] = -log(pe_v) / c.kfavd;
+    z[ZR_FD] = fd; z[ZR_X] = x;
+}
 
 __global__ void __launch_bounds__(GORT_EN_THREADS)
 energy_kernel(int n_sets, int n_geom, int n_wl, int geom_per_set, int spectra_per_set, gort_options opt,
               const double* __restrict__ structure, const double* __restrict__ lut,
               const double* __restrict__ angles, const double* __restrict__ gl /*[2][32]*/,
+              const double* __restrict__ zrec,
               const double* __restrict__ rleaf, const double* __restrict__ tleaf,
               const double* __restrict__ rsoil,
               double* __restrict__ albedo, double* __restrict__ favegt, double* __restrict__ fasoil)
@@ -427,7 +489,6 @@ energy_kernel(int n_sets, int n_geom, int n_wl, int geom_per_set, int spectra_pe
     __shared__ double part[5][GORT_EN_THREADS / 32];    // per-warp partial sums of the weighted coefficients
     __shared__ double coef[5];
     __shared__ double sunv[6];                          // fd mus t0 tp0 pe_s pn0_s
-    __shared__ double s_absc[GORT_NQUAD], s_wts[GORT_NQUAD];
 
     const long L = (long) n_sets * n_geom;
     const long line = blockIdx.x;
@@ -435,24 +496,55 @@ energy_kernel(int n_sets, int n_geom, int n_wl, int geom_per_set, int spectra_pe
     const long a = geom_per_set ? line : (line - (long) m * n_geom);
     const long na = geom_per_set ? L : n_geom;
     const int tid = threadIdx.x;
-    if (tid < GORT_NQUAD) { s_absc[tid] = gl[tid]; s_wts[tid] = gl[GORT_NQUAD + tid]; }
-    __syncthreads();
-
     const Canopy c = canopy_load(structure, n_sets, m, lut);
-    const Line g = line_from_degrees(angles[0 * na + a], angles[1 * na + a], angles[2 * na + a], angles[3 * na + a]);
-    const double fd = opt.use_fd ? opt.fd : cos(g.sza) / (cos(g.sza) + 0.09);
-    const double xr = 0.5 * (1. + 1.), xm = 0.5 * (1. - 1.);                     // gortt_albedo.c:82-83
-    const double ym = 0.5 * (2. * GORT_PI - 0.), yr = 0.5 * (2. * GORT_PI + 0.);  // :84-85
+    double fd;
     {
-        const int i = tid & 31, j = GORT_NQUAD / 2 + (tid >> 5);
-        double y = ym + yr * s_absc[i];                                          // :91
+        const int i = tid & 31, jj = tid >> 5;
+        const double* z = zrec + ((size_t) line * GORT_EN_NZ + jj) * GORT_EN_ZREC;      // same record for the whole warp
+        const double xr = 0.5 * (1. + 1.);
+        const double ym = 0.5 * (2. * GORT_PI - 0.), yr = 0.5 * (2. * GORT_PI + 0.);  // gortt_albedo.c:84-85
+        // azimuth of this node: saa after the reference's normalisation (gortt.c:253-274 via line_from_degrees)
+        const Line g = line_from_degrees(angles[0 * na + a], angles[1 * na + a], angles[2 * na + a], angles[3 * na + a]);
+        double y = ym + yr * gl[i];                                              // :91
         double vaa = y;
         for (int it = 0; it < 8 && vaa > 2 * GORT_PI; it++) vaa -= 2 * GORT_PI;  // :96
-        double raa = fold_raa(g.saa - vaa);                                      // :97-98
-        double x = xm + xr * s_absc[j];                                          // :103
-        double vza = acos(x);                                                    // :105
-        GeomRec r = geom_record(c, lut + (size_t) m * GORT_LUT_STRIDE, opt, vza, g.sza, raa, fd);
-        const double wn = (s_wts[j] * fabs(x) * xr) * (s_wts[i] * yr);           // :128-129, :132-133
+        const double raa = fold_raa(g.saa - vaa);                                // :97-98
+        double sr, cr;
+        sincos(raa, &sr, &cr);
+        Primed P;
+        P.vza_p = z[ZR_VZA_P]; P.sza_p = z[ZR_SZA_P];
+        P.t.ts = z[ZR_TS]; P.t.tv = z[ZR_TV]; P.t.secs = z[ZR_SECS]; P.t.secv = z[ZR_SECV];
+        P.t.cs = z[ZR_CS]; P.t.cv = z[ZR_CV]; P.t.ss = z[ZR_SS]; P.t.sv = z[ZR_SV];
+        CrownLite s;
+        s.Mv = z[ZR_MV]; s.theta_Mi = z[ZR_THETA_MI]; s.Gamma_v = z[ZR_GAMMA_V];
+        const double vza = z[ZR_VZA];
+        const bool vgs = fabs(vza) > fabs(g.sza);
+        const Pass pa = kc_pass(c, P, s, vgs, raa, cr, sr);
+        Tail tl;
+        tl.e_v = z[ZR_EV]; tl.e_s = z[ZR_ES]; tl.t0 = z[ZR_T0]; tl.beta = z[ZR_BETA];
+        // pair part of gortt_kuusk, gortt_brdf.c:650-702
+        Hot h;
+        h.pn0_s = z[ZR_PN0S]; h.pe_s = z[ZR_PES];
+        {
+            const double cos_xi = z[ZR_CSZ] * z[ZR_CVZ] + z[ZR_SSZ] * z[ZR_SVZ] * cr;
+            const double lsza = z[ZR_LSZA], lvza = z[ZR_LVZA];
+            const double arg = lsza * lsza + lvza * lvza - 2. * lsza * lvza * cos_xi;
+            double t1, t2;
+            if (arg > 0.0) {
+                double lsv = sqrt(arg);
+                t2 = (1.0 - exp(-lsv / c.r)) / (lsv / c.r);
+            } else {
+                t2 = 1.0;
+            }
+            if ((lsza * lvza) > 0.0) t1 = sqrt(lsza * lvza);
+            else t1 = 0.0;
+            const double H = exp(c.kfavd * t1 * t2);
+            h.kuusk = h.pe_s * z[ZR_PEV] * H;
+        }
+        fd = z[ZR_FD];
+        const GeomRec r = geom_combine(c, P, pa, z[ZR_F0F0], z[ZR_F180F180], tl, h, raa, fd);
+        const double x = z[ZR_X];
+        const double wn = (gl[GORT_NQUAD + GORT_NQUAD / 2 + jj] * fabs(x) * xr) * (gl[GORT_NQUAD + i] * yr);   // :128-129, :132-133
         double v[5] = {wn * r.cA, wn * r.Kc, wn * r.cG, wn * r.cZ, wn * r.Kt};
 #pragma unroll
         for (int k = 0; k < 5; k++) {
@@ -496,9 +588,17 @@ int launch_energy(gort_ctx *ctx, cudaStream_t s, const gort_shape &sh, const dou
     if (sh.n_sets <= 0 || sh.n_geom <= 0 || sh.n_wl <= 0)
         return set_error(ctx, GORT_ERR_INVALID, "gort_energy: n_sets, n_geom and n_wl must be positive");
     const long L = (long) sh.n_sets * sh.n_geom;
+    double *zrec = (double *) workspace(ctx, sizeof(double) * GORT_EN_ZREC * GORT_EN_NZ * (size_t) L);
+    if (!zrec) return GORT_ERR_NOMEM;
+    {
+        const long items = L * GORT_EN_NZ;
+        energy_zenith_kernel<<<(unsigned) ((items + 127) / 128), 128, 0, s>>>(sh.n_sets, sh.n_geom, sh.geom_per_set, sh.opt, structure,
+                                                                             lut, angles, ctx->d_gauleg, zrec);
+        ctx->launches++;
+    }
     energy_kernel<<<(unsigned) L, GORT_EN_THREADS, 0, s>>>(sh.n_sets, sh.n_geom, sh.n_wl, sh.geom_per_set,
                                                            sh.spectra_per_set, sh.opt, structure, lut, angles,
-                                                           ctx->d_gauleg, rleaf, tleaf, rsoil, albedo, favegt, fasoil);
+                                                           ctx->d_gauleg, zrec, rleaf, tleaf, rsoil, albedo, favegt, fasoil);
     ctx->launches++;
     return check_cuda(ctx, cudaGetLastError(), "gort_energy launch");
 }

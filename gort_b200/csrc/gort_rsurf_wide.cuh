@@ -55,6 +55,7 @@ struct WideArgs {
     int pdl;                      // launched with programmatic stream serialization after geom_kernel
     const unsigned long long *tile_flags;   // per 32-line tile: call number whose records geom_kernel has published
     unsigned long long call_no;
+    unsigned long long *fault;    // set to the call number if a bounded wait below ever expires
     unsigned long long *done;     // [grid size] per-CTA epoch: the last launch in which CTA k of this grid shape finished
     unsigned long long wait_target;   // epoch of the previous launch with the SAME grid shape and outputs (0: nothing to wait for)
     unsigned long long epoch;         // this launch's epoch
@@ -149,7 +150,7 @@ rsurf_wide_kernel(const WideArgs a)
                     if (v >= a.call_no) break;
                     __nanosleep(100);
                     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-                    if (t1 - t0 > 2000000000ull) break;           // 2 s: never hang
+                    if (t1 - t0 > 2000000000ull) { *a.fault = a.call_no; break; }   // 2 s: never hang; reported by gort_synchronize
                 }
             }
             __syncthreads();
@@ -227,7 +228,7 @@ rsurf_wide_kernel(const WideArgs a)
                         if (v >= a.wait_target) break;
                         __nanosleep(200);
                         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-                        if (t1 - t0 > 2000000000ull) break;       // 2 s: never hang on a broken predecessor
+                        if (t1 - t0 > 2000000000ull) { *a.fault = a.call_no; break; }   // 2 s: never hang; reported by gort_synchronize
                     }
                 }
                 __syncthreads();
