@@ -112,6 +112,32 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def bind_near_gpu(torch, local_rank):
+    """Pin this process to the CPUs of the GPU's NUMA node before any pinned host buffer is allocated: the e2e leg
+    is PCIe-bound (196 MB of D2H per step) and a buffer on the far socket costs ~20 % of the link rate.
+    Best effort; returns a description for the JSON line."""
+    info = {"gpu_node": None, "bound": False}
+    try:
+        p = torch.cuda.get_device_properties(local_rank)
+        bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        node = int(Path("/sys/bus/pci/devices/%s/numa_node" % bdf).read_text().strip())
+        info["gpu_node"] = node
+        if node < 0:
+            return info
+        cpus = set()
+        for part in Path("/sys/devices/system/node/node%d/cpulist" % node).read_text().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            info["bound"] = True
+            info["cpus"] = len(cpus)
+    except Exception as e:                      # noqa: BLE001 -- never fail the bench over placement
+        info["error"] = str(e)[:80]
+    return info
+
+
 def sweep_inputs(rank):
     from gort_b200 import workloads as wk
     w = wk.c2_hemisphere(sets=1, lai0=4.0 + 0.25 * rank)
@@ -213,6 +239,8 @@ def main():
         raise SystemExit("bench.py: no CUDA device; the GORT path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    all_cpus = os.sched_getaffinity(0)
+    numa = bind_near_gpu(torch, local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -323,7 +351,7 @@ def main():
                        "setup_not_timed": "gap-probability LUT + PROSPECT-D/Price spectra, computed once on the GPU"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(8 * evals_per_rank), "ms_per_step": e2e_ms / args.steps},
-            "gpu_launches": int(launches), "host_enqueue_ms_per_step": host_enqueue_ms,
+            "gpu_launches": int(launches), "host_enqueue_ms_per_step": host_enqueue_ms, "numa": numa,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "rsurf_wide_kernel", "achieved": achieved, "peak": hbm_peak,
                          "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": _ncu_traffic(),
@@ -340,6 +368,7 @@ def main():
         if world == 1 and not args.no_extras:
             out["extras"] = extras(g, torch, dev, ts, dfma)
         if world == 1 and not args.no_cpu_baseline:
+            os.sched_setaffinity(0, all_cpus)          # the CPU arm uses every host core
             out["cpu_baseline"] = cpu_baseline()
         print(json.dumps(out), flush=True)
 

@@ -249,7 +249,7 @@ __device__ double expected_single_crown_path(const Crown& c, const Ang& a, doubl
 }
 
 // lut_full_kernel: one CTA per GROUP of consecutive parameter sets that share (r, b, h1, h2) bit for bit
-// (capped at LUT_GROUP_CAP sets, chunk boundaries at multiples of the cap), one thread per zenith index t.
+// (capped at group_cap <= LUT_GROUP_CAP sets, chunk boundaries at multiples of the cap), one thread per zenith index t.
 //   phase 1, once per group: everything that depends on crown shape and zenith only -- the projected
 //            cross-section volumes v_g[h][t] (gortt_pn_kopen.c:24-32, :149-323), E[S] (:534-563), and for every
 //            entry height the tube-volume difference of :496 (Simpson rule, sphere/cylinder sections);
@@ -269,7 +269,7 @@ __device__ __forceinline__ bool same_shape(const double* __restrict__ st, size_t
 }
 
 __global__ void __launch_bounds__(LUT_THREADS)
-lut_full_kernel(int n_sets, const double* __restrict__ structure, double* __restrict__ lut)
+lut_full_kernel(int n_sets, int group_cap, const double* __restrict__ structure, double* __restrict__ lut)
 {
     __shared__ double s_hp[GORT_NLAYERS];        // height_p
     __shared__ double s_pn0[GORT_NTH];
@@ -279,9 +279,9 @@ lut_full_kernel(int n_sets, const double* __restrict__ structure, double* __rest
     const int t = threadIdx.x;
     const size_t N = (size_t) n_sets;
     // group heads: a set whose crown shape differs from its predecessor's, or that sits on a chunk boundary
-    if (m0 > 0 && (m0 % LUT_GROUP_CAP) != 0 && same_shape(structure, N, m0, m0 - 1)) return;
+    if (m0 > 0 && (m0 % group_cap) != 0 && same_shape(structure, N, m0, m0 - 1)) return;
     int m1 = m0 + 1;
-    while (m1 < n_sets && (m1 % LUT_GROUP_CAP) != 0 && same_shape(structure, N, m1, m1 - 1)) m1++;
+    while (m1 < n_sets && (m1 % group_cap) != 0 && same_shape(structure, N, m1, m1 - 1)) m1++;
 
     // ---- gortt_init_params, gortt.c:641-697: the shape-only part ------------------------------------
     const double r      = structure[1 * N + m0];
@@ -482,7 +482,14 @@ int launch_lut(gort_ctx *ctx, cudaStream_t s, int n_sets, const double *structur
         table_ready = true;
     }
     if (method == GORT_LUT_Q08) lut_q08_kernel<<<n_sets, LUT_THREADS, 0, s>>>(n_sets, structure, lut);
-    else lut_full_kernel<<<n_sets, LUT_THREADS, 0, s>>>(n_sets, structure, lut);
+    else {
+        // group cap: as large as possible (phase 1 is shared by the whole group) while the batch still yields
+        // enough groups to fill the GPU a few times over; results do not depend on it
+        int cap = n_sets / (ctx->sm_count * 12);
+        if (cap < 1) cap = 1;
+        if (cap > LUT_GROUP_CAP) cap = LUT_GROUP_CAP;
+        lut_full_kernel<<<n_sets, LUT_THREADS, 0, s>>>(n_sets, cap, structure, lut);
+    }
     ctx->launches++;
     return check_cuda(ctx, cudaGetLastError(), "gort_lut launch");
 }
