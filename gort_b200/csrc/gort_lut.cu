@@ -112,11 +112,11 @@ __device__ __noinline__ double triang(double b, double r, const Ang& a)
     const int m = LUT_NOINT;
     double h = .50 * (x0 - b) / (double) (float) m;
     double sum1 = 0.0;
-#pragma unroll 1
+#pragma unroll 4
     for (int i = 0; i < m; i++) sum1 += triang_fcn(b + (double) (float) (2 * i + 1) * h, b, r, a.t);
     double volume = 4.0 * sum1;
     double sum2 = 0.0;
-#pragma unroll 1
+#pragma unroll 4
     for (int i = 0; i < m - 1; i++) sum2 += triang_fcn(b + (double) (float) (2 * (i + 1)) * h, b, r, a.t);
     volume += 2.0 * sum2;
     volume += triang_fcn(x0, b, r, a.t);
@@ -272,11 +272,12 @@ __global__ void __launch_bounds__(LUT_THREADS)
 lut_full_kernel(int n_sets, int group_cap, const double* __restrict__ structure, double* __restrict__ lut)
 {
     __shared__ double s_hp[GORT_NLAYERS];        // height_p
-    __shared__ double s_pn0[GORT_NTH];
-    __shared__ double s_epg[GORT_NTH];
+    __shared__ double s_pn0[2][GORT_NTH];        // double-buffered over group members: one barrier per member
+    __shared__ double s_epg[2][GORT_NTH];
     __shared__ double s_sin2[GORT_NTH];
     const int m0 = blockIdx.x;
-    const int t = threadIdx.x;
+    const int tid = threadIdx.x;
+    const int t = tid;                           // zenith index
     const size_t N = (size_t) n_sets;
     // group heads: a set whose crown shape differs from its predecessor's, or that sits on a chunk boundary
     if (m0 > 0 && (m0 % group_cap) != 0 && same_shape(structure, N, m0, m0 - 1)) return;
@@ -300,9 +301,9 @@ lut_full_kernel(int n_sets, int group_cap, const double* __restrict__ structure,
     c.ds = dz;
     c.dz_p = dz / ellip;
     c.lv_p = 0.0; c.tau_p = 0.0;                 // per member, below
-    if (t < GORT_NLAYERS) {                                                      // gortt.c:778-781
-        double height = z2 - dz * (double) (GORT_NLAYERS - 1 - t);
-        s_hp[t] = height / ellip;
+    if (tid < GORT_NLAYERS) {                                                    // gortt.c:778-781
+        double height = z2 - dz * (double) (GORT_NLAYERS - 1 - tid);
+        s_hp[tid] = height / ellip;
     }
     __syncthreads();
 
@@ -336,6 +337,7 @@ lut_full_kernel(int n_sets, int group_cap, const double* __restrict__ structure,
 
     // ---- members of the group -----------------------------------------------------------------------
     for (int m = m0; m < m1; m++) {
+        const int pb = (m - m0) & 1;
         const double lambda = structure[0 * N + m];
         const double favd   = structure[5 * N + m];
         const double lv = lambda / (h2 - h1);
@@ -386,8 +388,8 @@ lut_full_kernel(int n_sets, int group_cap, const double* __restrict__ structure,
                     }
                 }
             }
-            s_pn0[t] = pn0_0;
-            s_epg[t] = e_t;
+            s_pn0[pb][t] = pn0_0;
+            s_epg[pb][t] = e_t;
             double* o = lut + (size_t) m * GORT_LUT_STRIDE;
             o[t] = pn0_0;
             o[GORT_NTH + t] = e_t;
@@ -397,24 +399,25 @@ lut_full_kernel(int n_sets, int group_cap, const double* __restrict__ structure,
         // ---- gortt_calc_kopen, gortt_pn_kopen.c:351-375 for h = 0: the trapezoid panels
         //      (f_i + f_{i-1})/2 * dth, i = 1..90, summed by warp 0 (three panels per lane, then a shuffle tree;
         //      the reference adds them left to right -- same panels, different association) ----
-        if (t < 32) {
+        if (tid < 32) {
             double ko = 0.0, ke = 0.0;
-            for (int i = 1 + t; i < GORT_NTH; i += 32) {
-                ko += (s_pn0[i] * s_sin2[i] + s_pn0[i - 1] * s_sin2[i - 1]) / 2.0 * dth;
-                ke += (s_epg[i] * s_sin2[i] + s_epg[i - 1] * s_sin2[i - 1]) / 2.0 * dth;
+            for (int i = 1 + tid; i < GORT_NTH; i += 32) {
+                ko += (s_pn0[pb][i] * s_sin2[i] + s_pn0[pb][i - 1] * s_sin2[i - 1]) / 2.0 * dth;
+                ke += (s_epg[pb][i] * s_sin2[i] + s_epg[pb][i - 1] * s_sin2[i - 1]) / 2.0 * dth;
             }
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) {
                 ko += __shfl_xor_sync(0xffffffffu, ko, off);
                 ke += __shfl_xor_sync(0xffffffffu, ke, off);
             }
-            if (t == 0) {
+            if (tid == 0) {
                 double* o = lut + (size_t) m * GORT_LUT_STRIDE;
                 o[2 * GORT_NTH] = ko;
                 o[2 * GORT_NTH + 1] = ke;
             }
         }
-        __syncthreads();
+        // no second barrier: the next member writes the other buffer, and the barrier after ITS crown-count loop
+        // orders this trapezoid before the buffer is reused two members on
     }
 }
 
