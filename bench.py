@@ -438,6 +438,14 @@ def extras(g, torch, dev, ts, dfma_tflops):
                       "evals_per_s_including_lut_and_spectra": evals / ((lut_ms + sp_ms + br_ms) * 1e-3),
                       "finite_fraction": float(torch.isfinite(d_out).double().mean())}
 
+    # C4a: the same ensemble with the crown structure shared and only LAI varying (favd): one crown-geometry phase
+    # and one crown-count loop per LUT sub-group
+    wa = wk.c4_enkf(vary_structure=False)
+    d_sta = T(wa["structure"])
+    luta_ms = _time_dev(torch, ts, lambda: g.lut_dev(d_sta, d_lut, stream=stream), reps=2)
+    res["c4_enkf"]["lai_only_lut_kernel_ms"] = luta_ms
+    res["c4_enkf"]["lai_only_luts_per_s"] = M / (luta_ms * 1e-3)
+
     # C5: LUT generation over the structural grid (131 072 parameter sets), one GPU's share = all of it here
     st = wk.c5_lut_grid()["structure"]
     M = st.shape[1]

@@ -253,13 +253,15 @@ __device__ double expected_single_crown_path(const Crown& c, const Ang& a, doubl
 //   phase 1, once per group: everything that depends on crown shape and zenith only -- the projected
 //            cross-section volumes v_g[h][t] (gortt_pn_kopen.c:24-32, :149-323), E[S] (:534-563), and for every
 //            entry height the tube-volume difference of :496 (Simpson rule, sphere/cylinder sections);
-//   phase 2, per member: p_n0 = exp(-lv' v_g) (stem density), the crown-count loop (:489-527) and the
-//            within-crown gap sum (favd), then the trapezoid rule of gortt_calc_kopen by thread 0.
+//   phase 2, per sub-group of up to 8 members that also share the stem density: p_n0 = exp(-lv' v_g) and the
+//            crown-count loop (:489-527) once; per member only the bin attenuations exp(-s_bin tau') (favd) and the
+//            within-crown gap sums; then the trapezoid rule of gortt_calc_kopen, one warp per member.
 // Phase 1 is ~2/3 of a set's instructions, so LUT grids and ensembles that vary stem density / leaf area over
 // fixed crown shapes (BASELINE.json configs 4a and 5) pay it once per group instead of once per set.
 #define LUT_GROUP_CAP 64
 // 1/n!, n = 0..30 (the reference tabulates n! in gortt.c:752-754 and divides)
 __constant__ double c_inv_fact[LUT_MAXCROWNS + 1];
+#define LUT_SUB 8                       // members per sub-group (same shape AND same stem density)
 #define LUT_NSP (GORT_NLAYERS - 2)     // entry heights sp_i = 1 .. 13 (sp_i = 14 contributes p_s0 = 0)
 
 __device__ __forceinline__ bool same_shape(const double* __restrict__ st, size_t n, int a, int b)
@@ -268,12 +270,13 @@ __device__ __forceinline__ bool same_shape(const double* __restrict__ st, size_t
            st[3 * n + a] == st[3 * n + b] && st[4 * n + a] == st[4 * n + b];
 }
 
+template <int SUB>
 __global__ void __launch_bounds__(LUT_THREADS)
 lut_full_kernel(int n_sets, int group_cap, const double* __restrict__ structure, double* __restrict__ lut)
 {
     __shared__ double s_hp[GORT_NLAYERS];        // height_p
-    __shared__ double s_pn0[2][GORT_NTH];        // double-buffered over group members: one barrier per member
-    __shared__ double s_epg[2][GORT_NTH];
+    __shared__ double s_pn0[GORT_NTH];
+    __shared__ double s_epg[SUB][GORT_NTH];
     __shared__ double s_sin2[GORT_NTH];
     const int m0 = blockIdx.x;
     const int tid = threadIdx.x;
@@ -283,6 +286,13 @@ lut_full_kernel(int n_sets, int group_cap, const double* __restrict__ structure,
     if (m0 > 0 && (m0 % group_cap) != 0 && same_shape(structure, N, m0, m0 - 1)) return;
     int m1 = m0 + 1;
     while (m1 < n_sets && (m1 % group_cap) != 0 && same_shape(structure, N, m1, m1 - 1)) m1++;
+    // two instantiations share the work: SUB = 1 (94 registers) takes the groups whose members all differ in stem
+    // density -- in particular every single-set group --, SUB = LUT_SUB takes the groups that start with a
+    // sub-group (same stem density, favd varying)
+    {
+        const bool shares = (m1 - m0 >= 2) && structure[0 * N + m0] == structure[0 * N + m0 + 1];
+        if ((SUB == 1) == shares) return;
+    }
 
     // ---- gortt_init_params, gortt.c:641-697: the shape-only part ------------------------------------
     const double r      = structure[1 * N + m0];
@@ -335,16 +345,25 @@ lut_full_kernel(int n_sets, int group_cap, const double* __restrict__ structure,
         }
     }
 
-    // ---- members of the group -----------------------------------------------------------------------
-    for (int m = m0; m < m1; m++) {
-        const int pb = (m - m0) & 1;
-        const double lambda = structure[0 * N + m];
-        const double favd   = structure[5 * N + m];
+    // ---- members of the group, in sub-groups of up to SUB consecutive members that also share the stem
+    //      density: p_n0, P(n) and the bin sequence depend on lambda only, favd enters through the bin attenuation
+    //      exp(-s_bin tau') alone (gortt_pn_kopen.c:1110-1114), so the crown-count loop runs once per sub-group
+    //      and only the attenuations and the sums are per member ----
+    for (int ms = m0; ms < m1;) {
+        const double lambda = structure[0 * N + ms];
+        int nj = 1;
+        while (nj < SUB && ms + nj < m1 && structure[0 * N + ms + nj] == lambda) nj++;
         const double lv = lambda / (h2 - h1);
-        const double favd_p = favd * ellip;
-        const double tau_p = 0.5 * favd_p;
         const double lv_p = lv * ellip;
-        double e_t = 0.0, pn0_0 = 0.0;
+        double tau[SUB], e_t[SUB], w_bin[SUB];
+#pragma unroll
+        for (int j = 0; j < SUB; j++) {
+            const double favd = structure[5 * N + ms + (j < nj ? j : 0)];
+            const double favd_p = favd * ellip;
+            tau[j] = 0.5 * favd_p;
+            e_t[j] = 0.0; w_bin[j] = 0.0;
+        }
+        double pn0_0 = 0.0;
         if (t < GORT_NTH) {
             double pn0_hi = exp(-1.0 * lv_p * vg[GORT_NLAYERS - 1]);             // p_n0[14][t]
             pn0_0 = exp(-1.0 * lv_p * vg[0]);                                    // gortt_pn_kopen.c:30
@@ -371,7 +390,6 @@ lut_full_kernel(int n_sets, int group_cap, const double* __restrict__ structure,
                     const double q = exp(-x);
                     double pw = 1.0, qn = 1.0;
                     int last_idx = -1;
-                    double last_w = 0.0;
 #pragma unroll 1
                     for (int n = 1; n <= LUT_MAXCROWNS; n++) {                   // :489
                         pw *= temp1;                                             // temp1^n
@@ -383,41 +401,54 @@ lut_full_kernel(int n_sets, int group_cap, const double* __restrict__ structure,
                         const int idx = (int) u;
                         // gortt_calc_epgap + gortt_calc_pgap, :1110-1114, :1138; the bin's attenuation is
                         // re-used while consecutive crown counts fall into the same bin (s saturates at s')
-                        if (idx != last_idx) { last_w = exp(-((double) idx * c.ds) * tau_p); last_idx = idx; }
-                        e_t += last_w * (P_n * P_s_p);
+                        if (idx != last_idx) {
+                            const double sbin = (double) idx * c.ds;
+#pragma unroll
+                            for (int j = 0; j < SUB; j++) if (j < nj) w_bin[j] = exp(-sbin * tau[j]);
+                            last_idx = idx;
+                        }
+                        const double wgt = P_n * P_s_p;
+#pragma unroll
+                        for (int j = 0; j < SUB; j++) e_t[j] += w_bin[j] * wgt;
                     }
                 }
             }
-            s_pn0[pb][t] = pn0_0;
-            s_epg[pb][t] = e_t;
-            double* o = lut + (size_t) m * GORT_LUT_STRIDE;
-            o[t] = pn0_0;
-            o[GORT_NTH + t] = e_t;
+            s_pn0[t] = pn0_0;
+#pragma unroll
+            for (int j = 0; j < SUB; j++) {
+                if (j < nj) {
+                    s_epg[j][t] = e_t[j];
+                    double* o = lut + (size_t) (ms + j) * GORT_LUT_STRIDE;
+                    o[t] = pn0_0;
+                    o[GORT_NTH + t] = e_t[j];
+                }
+            }
         }
         __syncthreads();
 
         // ---- gortt_calc_kopen, gortt_pn_kopen.c:351-375 for h = 0: the trapezoid panels
-        //      (f_i + f_{i-1})/2 * dth, i = 1..90, summed by warp 0 (three panels per lane, then a shuffle tree;
-        //      the reference adds them left to right -- same panels, different association) ----
-        if (tid < 32) {
+        //      (f_i + f_{i-1})/2 * dth, i = 1..90, summed by one warp per member (three panels per lane, then a
+        //      shuffle tree; the reference adds them left to right -- same panels, different association) ----
+        for (int j = tid >> 5; j < nj; j += LUT_THREADS / 32) {
+            const int lane = tid & 31;
             double ko = 0.0, ke = 0.0;
-            for (int i = 1 + tid; i < GORT_NTH; i += 32) {
-                ko += (s_pn0[pb][i] * s_sin2[i] + s_pn0[pb][i - 1] * s_sin2[i - 1]) / 2.0 * dth;
-                ke += (s_epg[pb][i] * s_sin2[i] + s_epg[pb][i - 1] * s_sin2[i - 1]) / 2.0 * dth;
+            for (int i = 1 + lane; i < GORT_NTH; i += 32) {
+                ko += (s_pn0[i] * s_sin2[i] + s_pn0[i - 1] * s_sin2[i - 1]) / 2.0 * dth;
+                ke += (s_epg[j][i] * s_sin2[i] + s_epg[j][i - 1] * s_sin2[i - 1]) / 2.0 * dth;
             }
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) {
                 ko += __shfl_xor_sync(0xffffffffu, ko, off);
                 ke += __shfl_xor_sync(0xffffffffu, ke, off);
             }
-            if (tid == 0) {
-                double* o = lut + (size_t) m * GORT_LUT_STRIDE;
+            if (lane == 0) {
+                double* o = lut + (size_t) (ms + j) * GORT_LUT_STRIDE;
                 o[2 * GORT_NTH] = ko;
                 o[2 * GORT_NTH + 1] = ke;
             }
         }
-        // no second barrier: the next member writes the other buffer, and the barrier after ITS crown-count loop
-        // orders this trapezoid before the buffer is reused two members on
+        __syncthreads();             // the next sub-group overwrites s_pn0 / s_epg
+        ms += nj;
     }
 }
 
@@ -491,7 +522,9 @@ int launch_lut(gort_ctx *ctx, cudaStream_t s, int n_sets, const double *structur
         int cap = n_sets / (ctx->sm_count * 12);
         if (cap < 1) cap = 1;
         if (cap > LUT_GROUP_CAP) cap = LUT_GROUP_CAP;
-        lut_full_kernel<<<n_sets, LUT_THREADS, 0, s>>>(n_sets, cap, structure, lut);
+        lut_full_kernel<1><<<n_sets, LUT_THREADS, 0, s>>>(n_sets, cap, structure, lut);
+        lut_full_kernel<LUT_SUB><<<n_sets, LUT_THREADS, 0, s>>>(n_sets, cap, structure, lut);
+        ctx->launches++;
     }
     ctx->launches++;
     return check_cuda(ctx, cudaGetLastError(), "gort_lut launch");
