@@ -200,12 +200,7 @@ static int launch_wide(gort_ctx *ctx, cudaStream_t s, const gort_shape &sh, long
         }
     }
     // one resident wave: grid.y contiguous line ranges so that n_chunks * grid.y ~ SMs * occupancy
-    // one CTA slot per SM is left free (when there are at least two): the next call's CTAs move into it while
-    // this launch is still storing, so their start-up (leaf terms, record staging, sun terms) is off the
-    // store stream's critical path
-    static int spare = getenv("GORT_WIDE_SPARE") ? atoi(getenv("GORT_WIDE_SPARE")) : 0;
-    const int occ_used = (occ > spare) ? occ - spare : occ;
-    long nby = ((long) ctx->sm_count * occ_used) / n_chunks;
+    long nby = ((long) ctx->sm_count * occ) / n_chunks;
     if (nby < 1) nby = 1;
     if (nby > L) nby = L;
     a.lines_per_cta = (L + nby - 1) / nby;
@@ -277,6 +272,8 @@ int launch_brdf(gort_ctx *ctx, cudaStream_t s, const gort_shape &sh, const doubl
     const long L = (long) sh.n_sets * sh.n_geom;
     const long pitch = sh.out_pitch > 0 ? sh.out_pitch : sh.n_wl;
     if (pitch < sh.n_wl) return set_error(ctx, GORT_ERR_INVALID, "gort_brdf: out_pitch smaller than n_wl");
+    // development switches (A/B measurements in DESIGN.md): GORT_NO_PDL runs the two kernels of a call strictly one
+    // after the other, GORT_NO_XCALL keeps the overlap inside a call but not across calls
     static int use_pdl = getenv("GORT_NO_PDL") ? 0 : 1;
     static int use_xcall = getenv("GORT_NO_XCALL") ? 0 : 1;
     if (!ctx->d_done) {
