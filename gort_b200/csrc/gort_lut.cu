@@ -330,8 +330,32 @@ lut_full_kernel(int n_sets, int group_cap, const double* __restrict__ structure,
         if (a.th >= GORT_PI / 2.0) a.th = GORT_PI / 2.0 - 1.0 * GORT_PI / 180.0;
         a.s = sin(a.th); a.c = cos(a.th); a.t = tan(a.th);
         s_sin2[t] = sin(2.0 * theta);
+        // v_g[h][t], gortt_pn_kopen.c:29, :149-167: midpoint rule over the crown-centre height z of the projected
+        // cross-section of a crown centred at z seen from layer height h.  The cross-section depends on h - z
+        // only, the layer heights and the midpoints are both dz' apart, so the 15 x K evaluations take only
+        // 14 + K distinct values: each is evaluated once (at its first (h, z) pair) and the 15 sums are formed
+        // in the reference's order.  (The other pairs differ from it by the rounding of h - z, ~1e-16.)
+        {
+            double zk[16], A[32];
+            int K = 0;
+            for (double z = c.h1_p + c.dz_p / 2.0; z <= c.h2_p && K < 16; z += c.dz_p) zk[K++] = z;   // :162, running sum
+            if (K >= 1 && K < 16) {
 #pragma unroll 1
-        for (int h = 0; h < GORT_NLAYERS; h++) vg[h] = proj_volume(c, a, s_hp[h]);       // gortt_pn_kopen.c:29
+                for (int j = 0; j < GORT_NLAYERS + K - 1; j++) {
+                    const int i = max(0, j - (K - 1)), k = i - (j - (K - 1));
+                    A[j] = cross_section(c, a, s_hp[i], zk[k]);
+                }
+#pragma unroll 1
+                for (int h = 0; h < GORT_NLAYERS; h++) {
+                    double vol = 0.0;
+                    for (int k = 0; k < K; k++) vol += A[h - k + K - 1] * (c.dz_p);
+                    vg[h] = vol;
+                }
+            } else {
+#pragma unroll 1
+                for (int h = 0; h < GORT_NLAYERS; h++) vg[h] = proj_volume(c, a, s_hp[h]);
+            }
+        }
         if (t < GORT_NTH - 1) {                                                  // :1099
             const double hp0 = s_hp[0];
             es = expected_single_crown_path(c, a, hp0);                          // :445
