@@ -114,6 +114,50 @@ geom_kernel(int n_sets, int n_geom, int geom_per_set, gort_options opt,
 }
 
 // ------------------------------------------------------------------------------------------------
+// geom_lines_kernel: the same record, one thread per line.  With hundreds of thousands of lines (ensembles: 10^5
+// members x 16 geometries) the GPU is full and throughput counts, not the latency of one line; the role split of
+// geom_kernel repeats the primed trig and the crown terms in four warps (1.8x the instructions), so large batches
+// take this kernel instead.  Same device functions in the same order: same bits.
+__global__ void __launch_bounds__(128)
+geom_lines_kernel(int n_sets, int n_geom, int geom_per_set, gort_options opt,
+                  const double* __restrict__ structure, const double* __restrict__ lut,
+                  const double* __restrict__ angles, double* __restrict__ rec, double* __restrict__ kprop,
+                  unsigned long long* __restrict__ tile_flags, unsigned long long call_no)
+{
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const long L = (long) n_sets * n_geom;
+    const long line = (long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (line < L) {
+        const int m = (int) (line / n_geom);
+        const long a = geom_per_set ? line : (line - (long) m * n_geom);
+        const long na = geom_per_set ? L : n_geom;
+        const Canopy c = canopy_load(structure, n_sets, m, lut);
+        const Line g = line_from_degrees(angles[0 * na + a], angles[1 * na + a], angles[2 * na + a], angles[3 * na + a]);
+        const double fd = opt.use_fd ? opt.fd : cos(g.sza) / (cos(g.sza) + 0.09);       // gortt.c:290-291
+        const GeomRec r = geom_record(c, lut + (size_t) m * GORT_LUT_STRIDE, opt, g.vza, g.sza, g.raa, fd);
+        int flags = 0;
+        if (line % n_geom == 0) flags = 3;
+        else if (fabs(angles[2 * na + a]) != fabs(angles[2 * na + a - 1])) flags = 1;
+        double2* o = reinterpret_cast<double2*>(rec + (size_t) line * GORT_REC_STRIDE);
+        o[0] = make_double2(r.cA, r.Kc);   o[1] = make_double2(r.cG, r.cZ);
+        o[2] = make_double2(r.Kt, __longlong_as_double((long long) flags));
+        o[3] = make_double2(r.q, r.fd);
+        o[4] = make_double2(r.mus, r.t0);  o[5] = make_double2(r.tp0, r.pe_s);
+        o[6] = make_double2(r.Kpg, r.Kpz); o[7] = make_double2(r.Kg, r.Kz);
+        if (kprop) {
+            kprop[4 * line + 0] = r.Kc; kprop[4 * line + 1] = r.Kg;
+            kprop[4 * line + 2] = r.Kt; kprop[4 * line + 3] = r.Kz;
+        }
+    }
+    // a warp is one 32-line tile
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0 && (line >> 5) <= ((L - 1) >> 5)) {
+        __threadfence();
+        asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(tile_flags + (line >> 5)), "l"(call_no) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
 rsurf_flat_kernel(int n_sets, int n_geom, int n_wl, int spectra_per_set, long pitch,
                   const double* __restrict__ structure, const double* __restrict__ lut,
@@ -345,8 +389,18 @@ int launch_brdf(gort_ctx *ctx, cudaStream_t s, const gort_shape &sh, const doubl
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
         cfg.numAttrs = early_geom ? 1 : 0;
-        cudaError_t e = cudaLaunchKernelEx(&cfg, geom_kernel, sh.n_sets, sh.n_geom, sh.geom_per_set, sh.opt,
-                                           structure, lut, angles, rec, kprop, ctx->d_tile_flags, ctx->call_no);
+        // enough lines to fill the GPU several times over: one thread per line (see geom_lines_kernel)
+        const bool by_line = L >= 64L * 4 * ctx->sm_count;
+        cudaError_t e;
+        if (by_line) {
+            cfg.gridDim = dim3((unsigned) ((L + 127) / 128));
+            cfg.blockDim = dim3(128);
+            e = cudaLaunchKernelEx(&cfg, geom_lines_kernel, sh.n_sets, sh.n_geom, sh.geom_per_set, sh.opt,
+                                   structure, lut, angles, rec, kprop, ctx->d_tile_flags, ctx->call_no);
+        } else {
+            e = cudaLaunchKernelEx(&cfg, geom_kernel, sh.n_sets, sh.n_geom, sh.geom_per_set, sh.opt,
+                                   structure, lut, angles, rec, kprop, ctx->d_tile_flags, ctx->call_no);
+        }
         if (e != cudaSuccess) return check_cuda(ctx, e, "geom_kernel launch");
         ctx->launches++;
     }
