@@ -375,10 +375,10 @@ int launch_brdf(gort_ctx *ctx, cudaStream_t s, const gort_shape &sh, const doubl
         // the per-wavelength kernel that follows needs a large shared-memory carve-out; an SM only changes its
         // carve-out when idle, so ask for the same one here or the dependent kernel's CTAs could not join this
         // kernel's CTAs on an SM (measured: without it they entered only as geom_kernel's CTAs left)
-        static bool carve_set = false;
-        if (!carve_set) {
+        if (!ctx->geom_carveout_set) {            // per device, so per context
             cudaFuncSetAttribute(geom_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-            carve_set = true;
+            cudaFuncSetAttribute(geom_lines_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            ctx->geom_carveout_set = 1;
         }
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned) blocks);

@@ -41,6 +41,7 @@ struct gort_ctx {
     cudaEvent_t xstream_ev;            // orders BRDF calls issued on different streams
     struct { int key_lpt, key_scomp, key_minb, key_wl, key_threads; int occ; } wide_plan[8];
     int n_wide_plan;
+    int geom_carveout_set;
     // optional per-kernel event timing of the BRDF path (gort_profile_begin/end)
     cudaEvent_t *prof_ev;  // [3 * prof_cap]
     int prof_cap, prof_n;

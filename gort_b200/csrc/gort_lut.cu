@@ -259,8 +259,39 @@ __device__ double expected_single_crown_path(const Crown& c, const Ang& a, doubl
 // Phase 1 is ~2/3 of a set's instructions, so LUT grids and ensembles that vary stem density / leaf area over
 // fixed crown shapes (BASELINE.json configs 4a and 5) pay it once per group instead of once per set.
 #define LUT_GROUP_CAP 64
-// 1/n!, n = 0..30 (the reference tabulates n! in gortt.c:752-754 and divides)
-__constant__ double c_inv_fact[LUT_MAXCROWNS + 1];
+// 1/n!, n = 0..30, each the FP64 quotient 1.0 / n! (the reference tabulates n! in gortt.c:752-754 and divides)
+__constant__ double c_inv_fact[LUT_MAXCROWNS + 1] = {
+    1.0,
+    1.0,
+    0.5,
+    0.16666666666666666,
+    0.041666666666666664,
+    0.008333333333333333,
+    0.001388888888888889,
+    0.0001984126984126984,
+    2.48015873015873e-05,
+    2.7557319223985893e-06,
+    2.755731922398589e-07,
+    2.505210838544172e-08,
+    2.08767569878681e-09,
+    1.6059043836821613e-10,
+    1.1470745597729725e-11,
+    7.647163731819816e-13,
+    4.779477332387385e-14,
+    2.8114572543455206e-15,
+    1.5619206968586225e-16,
+    8.22063524662433e-18,
+    4.110317623312165e-19,
+    1.9572941063391263e-20,
+    8.896791392450574e-22,
+    3.8681701706306835e-23,
+    1.6117375710961184e-24,
+    6.446950284384474e-26,
+    2.4795962632247972e-27,
+    9.183689863795546e-29,
+    3.2798892370698385e-30,
+    1.1309962886447718e-31,
+    3.769987628815906e-33};
 #define LUT_SUB 8                       // members per sub-group (same shape AND same stem density)
 #define LUT_NSP (GORT_NLAYERS - 2)     // entry heights sp_i = 1 .. 13 (sp_i = 14 contributes p_s0 = 0)
 
@@ -530,15 +561,6 @@ lut_q08_kernel(int n_sets, const double* __restrict__ structure, double* __restr
 
 int launch_lut(gort_ctx *ctx, cudaStream_t s, int n_sets, const double *structure, int method, double *lut)
 {
-    static bool table_ready = false;
-    if (!table_ready) {
-        double h[LUT_MAXCROWNS + 1], f = 1.0;
-        h[0] = 1.0;
-        for (int n = 1; n <= LUT_MAXCROWNS; n++) { f *= (double) n; h[n] = 1.0 / f; }
-        cudaError_t e = cudaMemcpyToSymbol(c_inv_fact, h, sizeof h);
-        if (e != cudaSuccess) return check_cuda(ctx, e, "LUT factorial table");
-        table_ready = true;
-    }
     if (method == GORT_LUT_Q08) lut_q08_kernel<<<n_sets, LUT_THREADS, 0, s>>>(n_sets, structure, lut);
     else {
         // group cap: as large as possible (phase 1 is shared by the whole group) while the batch still yields

@@ -24,6 +24,7 @@
 #include <string.h>
 #include <strings.h>
 #include "gort_b200.h"
+#include "fastfmt.h"
 
 typedef struct {
     /* structure, gortt.c:67-72 */
@@ -298,22 +299,37 @@ int main(int argc, char **argv)
             if (gort_energy_batch(ctx, &sh, st, lut, soa, rleaf, tleaf, rsoil, alb, fv, fs) != GORT_OK)
                 die_gort(argv[0], ctx, "energy balance");
         }
-        for (int i = 0; i < na; i++) {                  /* gortt.c:310-327 */
+        /* gortt.c:310-327; same bytes as the reference's printf("%f ") calls, through a fast formatter */
+        gort_out *out = (gort_out *) malloc(sizeof(gort_out));
+        if (!out) { fprintf(stderr, "%s: out of memory\n", argv[0]); exit(EXIT_FAILURE); }
+        fflush(stdout);
+        out->fp = stdout; out->n = 0;
+        for (int i = 0; i < na; i++) {
             const double *a4 = ang + 4 * (size_t) i;
-            printf("%f %f %f %f ", a4[0], a4[1], a4[2], a4[3]);
+            for (int q = 0; q < 4; q++) gort_out_f(out, a4[q]);
             for (int k = 0; k < nw; k++) {
                 size_t o = (size_t) i * nw + k;
-                printf("%f ", rsurf[o]);
-                if (c.prnspec) printf("{ %f %f %f %f } ", scomp[4 * o], scomp[4 * o + 1], scomp[4 * o + 2], scomp[4 * o + 3]);
+                gort_out_f(out, rsurf[o]);
+                if (c.prnspec) {
+                    gort_out_str(out, "{ ");
+                    for (int q = 0; q < 4; q++) gort_out_f(out, scomp[4 * o + q]);
+                    gort_out_str(out, "} ");
+                }
             }
-            if (c.prnprop) printf("[ %f %f %f %f ] ", kprop[4 * i], kprop[4 * i + 1], kprop[4 * i + 2], kprop[4 * i + 3]);
+            if (c.prnprop) {
+                gort_out_str(out, "[ ");
+                for (int q = 0; q < 4; q++) gort_out_f(out, kprop[4 * (size_t) i + q]);
+                gort_out_str(out, "] ");
+            }
             if (c.energy)
                 for (int k = 0; k < nw; k++) {
                     size_t o = (size_t) i * nw + k;
-                    printf("%f %f %f ", alb[o], fv[o], fs[o]);
+                    gort_out_f(out, alb[o]); gort_out_f(out, fv[o]); gort_out_f(out, fs[o]);
                 }
-            printf("\n");
+            gort_out_str(out, "\n");
         }
+        gort_out_flush(out);
+        free(out);
         free(soa); free(rsurf); free(scomp); free(kprop); free(alb); free(fv); free(fs);
     } else if (na > 0) {
         for (int i = 0; i < na; i++) {                  /* no wavelengths: angles only */
