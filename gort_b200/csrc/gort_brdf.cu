@@ -1,16 +1,17 @@
 // gort_brdf.cu -- BRDF and energy-balance kernels (sm_100a, FP64, no tensor cores: nothing here
 // is a dense contraction).
 //
-//   geom_kernel        one thread per (parameter set, input line): everything gortt_rsurf does
-//                      before its wavelength loop (gortt.c:240-291, :424-449, gortt_brdf.c:7-238,
-//                      :638-702) -> 13-double geometry record, SoA in HBM.
-//   rsurf_wide_kernel  W >= 64: one CTA per (line tile, wavelength chunk); the tile's records are
-//                      staged in shared memory, each thread owns wavelengths and walks the lines,
-//                      re-deriving (set, lambda) terms only when the set changes and
-//                      (sun, lambda) terms only when the sun changes.  Coalesced FP64 stores.
-//   rsurf_flat_kernel  W < 64 (band sets): one thread per (line, band).
-//   energy_kernel      one CTA per (set, sun line): 512 quadrature nodes' records in shared
-//                      memory, lanes = azimuth nodes, warp-shuffle reduction (gortt_albedo.c).
+//   geom_kernel          everything gortt_rsurf does before its wavelength loop (gortt.c:240-291, :424-449,
+//                        gortt_brdf.c:7-238, :638-702) -> packed 128-byte line record in HBM.  32 lines x 5 role
+//                        warps per CTA (latency-bound: few lines); geom_lines_kernel is the one-thread-per-line
+//                        form for batches that fill the GPU (ensembles).  Both publish per-tile ready flags.
+//   rsurf_wide_kernel    W >= 64 (gort_rsurf_wide.cuh): one CTA per (wavelength chunk, contiguous line range);
+//                        (set, lambda) terms in shared memory, (sun, lambda) terms in registers, 5 FMAs and one
+//                        coalesced store per evaluation; pipelined with geom_kernel and across calls.
+//   rsurf_flat_kernel    W < 64 (band sets): one thread per (line, band).
+//   energy_zenith_kernel / energy_kernel   hemispherical quadrature for albedo / fAPAR (gortt_albedo.c): the
+//                        quadrature collapses onto five weighted sums of node coefficients.
+//   gauleg_kernel, dfma_kernel            Gauss-Legendre nodes; FP64 FMA microbenchmark.
 #include <stdio.h>
 #include <stdlib.h>
 #include "gort_device.cuh"
