@@ -538,7 +538,7 @@ energy_zenith_kernel(int n_sets, int n_geom, int geom_per_set, gort_options opt,
     z[ZR_FD] = fd; z[ZR_X] = x;
 }
 
-__global__ void __launch_bounds__(GORT_EN_THREADS)
+__global__ void __launch_bounds__(GORT_EN_THREADS, 2)
 energy_kernel(int n_sets, int n_geom, int n_wl, int geom_per_set, int spectra_per_set, gort_options opt,
               const double* __restrict__ structure, const double* __restrict__ lut,
               const double* __restrict__ angles, const double* __restrict__ gl /*[2][32]*/,
