@@ -119,7 +119,7 @@ geom_kernel(int n_sets, int n_geom, int geom_per_set, gort_options opt,
 // members x 16 geometries) the GPU is full and throughput counts, not the latency of one line; the role split of
 // geom_kernel repeats the primed trig and the crown terms in four warps (1.8x the instructions), so large batches
 // take this kernel instead.  Same device functions in the same order: same bits.
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 6)
 geom_lines_kernel(int n_sets, int n_geom, int geom_per_set, gort_options opt,
                   const double* __restrict__ structure, const double* __restrict__ lut,
                   const double* __restrict__ angles, double* __restrict__ rec, double* __restrict__ kprop,
