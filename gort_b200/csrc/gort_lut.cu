@@ -306,9 +306,6 @@ __global__ void __launch_bounds__(LUT_THREADS)
 lut_full_kernel(int n_sets, int group_cap, const double* __restrict__ structure, double* __restrict__ lut)
 {
     __shared__ double s_hp[GORT_NLAYERS];        // height_p
-    __shared__ double s_pn0[GORT_NTH];
-    __shared__ double s_epg[SUB][GORT_NTH];
-    __shared__ double s_sin2[GORT_NTH];
     const int m0 = blockIdx.x;
     const int tid = threadIdx.x;
     const int t = tid;                           // zenith index
@@ -360,7 +357,6 @@ lut_full_kernel(int n_sets, int group_cap, const double* __restrict__ structure,
         a.th = atan(tan(theta) * ellip);
         if (a.th >= GORT_PI / 2.0) a.th = GORT_PI / 2.0 - 1.0 * GORT_PI / 180.0;
         a.s = sin(a.th); a.c = cos(a.th); a.t = tan(a.th);
-        s_sin2[t] = sin(2.0 * theta);
         // v_g[h][t], gortt_pn_kopen.c:29, :149-167: midpoint rule over the crown-centre height z of the projected
         // cross-section of a crown centred at z seen from layer height h.  The cross-section depends on h - z
         // only, the layer heights and the midpoints are both dz' apart, so the 15 x K evaluations take only
@@ -468,41 +464,17 @@ lut_full_kernel(int n_sets, int group_cap, const double* __restrict__ structure,
                     }
                 }
             }
-            s_pn0[t] = pn0_0;
 #pragma unroll
             for (int j = 0; j < SUB; j++) {
                 if (j < nj) {
-                    s_epg[j][t] = e_t[j];
                     double* o = lut + (size_t) (ms + j) * GORT_LUT_STRIDE;
                     o[t] = pn0_0;
                     o[GORT_NTH + t] = e_t[j];
                 }
             }
         }
-        __syncthreads();
-
-        // ---- gortt_calc_kopen, gortt_pn_kopen.c:351-375 for h = 0: the trapezoid panels
-        //      (f_i + f_{i-1})/2 * dth, i = 1..90, summed by one warp per member (three panels per lane, then a
-        //      shuffle tree; the reference adds them left to right -- same panels, different association) ----
-        for (int j = tid >> 5; j < nj; j += LUT_THREADS / 32) {
-            const int lane = tid & 31;
-            double ko = 0.0, ke = 0.0;
-            for (int i = 1 + lane; i < GORT_NTH; i += 32) {
-                ko += (s_pn0[i] * s_sin2[i] + s_pn0[i - 1] * s_sin2[i - 1]) / 2.0 * dth;
-                ke += (s_epg[j][i] * s_sin2[i] + s_epg[j][i - 1] * s_sin2[i - 1]) / 2.0 * dth;
-            }
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) {
-                ko += __shfl_xor_sync(0xffffffffu, ko, off);
-                ke += __shfl_xor_sync(0xffffffffu, ke, off);
-            }
-            if (lane == 0) {
-                double* o = lut + (size_t) (ms + j) * GORT_LUT_STRIDE;
-                o[2 * GORT_NTH] = ko;
-                o[2 * GORT_NTH + 1] = ke;
-            }
-        }
-        __syncthreads();             // the next sub-group overwrites s_pn0 / s_epg
+        // the openness factors (trapezoid rule over the 91 zeniths just written) are formed by kopen_kernel: no
+        // barrier here, so a CTA's three warps -- whose zeniths differ in cost -- never wait for each other
         ms += nj;
     }
 }
@@ -559,6 +531,34 @@ lut_q08_kernel(int n_sets, const double* __restrict__ structure, double* __restr
     }
 }
 
+// gortt_calc_kopen, gortt_pn_kopen.c:351-375 for h = 0: k_open = trapezoid rule of p_n0 sin(2 theta) over the 91
+// zeniths, k_openep the same for epgap.  One warp per parameter set: the panels (f_i + f_{i-1})/2 * dth, i = 1..90,
+// three per lane, then a shuffle tree (the reference adds them left to right: same panels, different association).
+__global__ void __launch_bounds__(128)
+kopen_kernel(int n_sets, double* __restrict__ lut)
+{
+    const int m = (int) (((long) blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (m >= n_sets) return;
+    const int lane = threadIdx.x & 31;
+    const double dth = 1 * GORT_PI / 180.0;
+    double* o = lut + (size_t) m * GORT_LUT_STRIDE;
+    double ko = 0.0, ke = 0.0;
+    for (int i = 1 + lane; i < GORT_NTH; i += 32) {
+        double th1 = dth * (double) i, th0 = dth * (double) (i - 1);                 // gortt.c:783-787
+        if (th1 >= GORT_PI / 2.0) th1 = GORT_PI / 2.0 - 1.0 * GORT_PI / 180.0;
+        if (th0 >= GORT_PI / 2.0) th0 = GORT_PI / 2.0 - 1.0 * GORT_PI / 180.0;
+        const double s1 = sin(2.0 * th1), s0 = sin(2.0 * th0);
+        ko += (o[i] * s1 + o[i - 1] * s0) / 2.0 * dth;
+        ke += (o[GORT_NTH + i] * s1 + o[GORT_NTH + i - 1] * s0) / 2.0 * dth;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        ko += __shfl_xor_sync(0xffffffffu, ko, off);
+        ke += __shfl_xor_sync(0xffffffffu, ke, off);
+    }
+    if (lane == 0) { o[2 * GORT_NTH] = ko; o[2 * GORT_NTH + 1] = ke; }
+}
+
 int launch_lut(gort_ctx *ctx, cudaStream_t s, int n_sets, const double *structure, int method, double *lut)
 {
     if (method == GORT_LUT_Q08) lut_q08_kernel<<<n_sets, LUT_THREADS, 0, s>>>(n_sets, structure, lut);
@@ -570,7 +570,8 @@ int launch_lut(gort_ctx *ctx, cudaStream_t s, int n_sets, const double *structur
         if (cap > LUT_GROUP_CAP) cap = LUT_GROUP_CAP;
         lut_full_kernel<1><<<n_sets, LUT_THREADS, 0, s>>>(n_sets, cap, structure, lut);
         lut_full_kernel<LUT_SUB><<<n_sets, LUT_THREADS, 0, s>>>(n_sets, cap, structure, lut);
-        ctx->launches++;
+        kopen_kernel<<<(unsigned) (((long) n_sets * 32 + 127) / 128), 128, 0, s>>>(n_sets, lut);
+        ctx->launches += 2;
     }
     ctx->launches++;
     return check_cuda(ctx, cudaGetLastError(), "gort_lut launch");
