@@ -366,7 +366,10 @@ def main():
             "checksum": checksum,
         }
         if world == 1 and not args.no_extras:
-            out["extras"] = extras(g, torch, dev, ts, dfma)
+            try:
+                out["extras"] = extras(g, torch, dev, ts, dfma)
+            except Exception as e:                     # noqa: BLE001 -- the extras must never cost the main line
+                out["extras"] = {"error": "%s: %s" % (type(e).__name__, str(e)[:200])}
         if world == 1 and not args.no_cpu_baseline:
             os.sched_setaffinity(0, all_cpus)          # the CPU arm uses every host core
             out["cpu_baseline"] = cpu_baseline()
@@ -402,6 +405,24 @@ def extras(g, torch, dev, ts, dfma_tflops):
         tf = flops / (ms * 1e-3) / 1e12
         return {"bound": "fp64", "achieved": tf, "peak": dfma_tflops, "unit": "TFLOP/s", "frac": tf / dfma_tflops,
                 "peak_source": "in-library DFMA microbenchmark, same run"}
+
+    # C2 with component signatures ("-prnspec"): rsurf + C, G, T, Z = 40 B per evaluation, a quarter of the sweep
+    w = wk.c2_hemisphere()
+    G4 = w["angles"].shape[1] // 4
+    W = w["wavelength"].shape[0]
+    Wp = (W + 15) // 16 * 16
+    d_st, d_ang = T(w["structure"]), T(w["angles"][:, :G4])
+    d_lut = E(1, LUT_STRIDE); g.lut_dev(d_st, d_lut, stream=stream)
+    d_rl, d_tl, d_rs = E(1, W), E(1, W), E(1, W)
+    g.spectra_dev(T(w["leaf"]), T(w["soil"]), T(w["wavelength"]), d_rl, d_tl, d_rs, stream=stream)
+    d_r, d_sc = E(1, G4, Wp), E(1, G4, Wp, 4)
+    sc_ms = _time_dev(torch, ts, lambda: g.brdf_dev(d_st, d_lut, d_ang, d_rl[0], d_tl[0], d_rs[0], d_r, scomp=d_sc, stream=stream))
+    hbm, _ = load_peaks()
+    res["c2_prnspec"] = {"lines": G4, "wavelengths": W, "brdf_ms": sc_ms, "evals_per_s": G4 * W / (sc_ms * 1e-3),
+                         "roofline": {"bound": "hbm", "achieved": 40.0 * G4 * W / (sc_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                                      "frac": 40.0 * G4 * W / (sc_ms * 1e-3) / 1e9 / hbm,
+                                      "note": "geometry kernel + per-wavelength kernel of one isolated call, 40 B per evaluation"}}
+    del d_r, d_sc
 
     # C3: spectral albedo + fAPAR, 10^4 sets x 3 sun angles x 211 bands x 512 quadrature nodes
     w = wk.c3_albedo()
