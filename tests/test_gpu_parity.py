@@ -484,3 +484,26 @@ def test_small_and_degenerate_shapes(gort, oracle):
             assert_close(a[0], a_o, "albedo nw %d" % nw); assert_close(v[0], v_o, "favegt", rtol=1e-8); assert_close(s[0], s_o, "fasoil")
     with pytest.raises(gort_b200.GortError):
         gort.brdf(st, lut, np.zeros((4, 0)), np.zeros(3), np.zeros(3), np.zeros(3))
+
+
+def test_wide_kernel_many_lines_multiwave_geometry(gort, oracle):
+    """300 000 lines x 64 bands: the geometry kernel needs several waves of CTAs while the per-wavelength kernel,
+    launched as its programmatic dependent, waits on the per-tile flags -- results must not depend on it."""
+    rng = np.random.Generator(np.random.PCG64(321))
+    M, G, nw = 2, 150000, 64
+    st = wk.random_structures(rng, M)
+    leaf = wk.random_leaves(rng, M)
+    wl = np.sort(rng.uniform(400, 2500, nw))
+    sza = np.repeat(rng.uniform(0, 75, G // 50), 50); saa = np.repeat(rng.uniform(0, 360, G // 50), 50)
+    ang = np.stack([rng.uniform(0, 80, G), rng.uniform(0, 360, G), sza, saa])
+    lut = gort.lut(st)
+    rl, tl, rs = gort.spectra(leaf, np.repeat(wk.DEFAULT_SOIL.reshape(4, 1), M, axis=1), wl)
+    full = gort.brdf(st, lut, ang, rl, tl, rs)
+    assert full.shape == (M, G, nw) and np.isfinite(full).all()
+    for m in range(M):
+        for lo, hi in ((0, 777), (74990, 75100), (G - 513, G)):
+            part = gort.brdf(st[:, m:m + 1], lut[m:m + 1], ang[:, lo:hi], rl[m], tl[m], rs[m])
+            assert np.array_equal(part[0], full[m, lo:hi])
+        idx = np.arange(0, G, 2999)
+        r_o, _, _ = oracle.brdf(st[:, m], lut[m], ang[:, idx].T, rl[m], tl[m], rs[m])
+        assert_close(full[m, idx], r_o, "set %d" % m)
