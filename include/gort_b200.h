@@ -28,7 +28,9 @@
  *     i; the stores of call i+1 to a region start only after call i's stores to that region are complete), so
  *     their results are exactly those of running them one after the other.  The overlap is used only when no
  *     input of call i+1 lies inside an output buffer of call i; any other operation put on the stream between two
- *     calls (a copy, another kernel) orders them completely, as does switching streams.
+ *     calls (a copy, another kernel) orders them completely, as does switching streams.  The in-kernel waits of
+ *     this pipeline are bounded (2 s); should one ever expire, gort_synchronize() and the host-pointer entry points
+ *     return GORT_ERR_CUDA with the number of the affected call.
  */
 #ifndef GORT_B200_H
 #define GORT_B200_H
