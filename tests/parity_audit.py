@@ -1,0 +1,418 @@
+"""Audit-grade parity report -- TEST INFRASTRUCTURE, not product code.
+
+Compares the CUDA path (called through the C ABI) with the CPU checkers on the BASELINE.json configs and
+records, for every output and every band, what the metric asks for ("max rel err ... worst case reported per
+output band"):
+
+    n                     entries compared
+    max_rel_err           worst |x - ref| / max(|ref|, 1e-12) over ALL finite entries (excused ones included)
+    n_beyond_tol          entries beyond the 1e-9 tolerance
+    n_excused             of those, entries explained by the conditioning of the reference algorithm itself:
+                          |x - ref| <= 32 x (how far the restatement moves under a 1-ULP libm, oracle/ulp_libm_shim.c)
+    worst_excused_rel     the largest such excused error
+    n_unexplained         beyond tolerance and not excused -- any non-zero value FAILS the audit
+    nonfinite_ref / nonfinite_mismatch   NaN / Inf entries of the reference, and positions where the two disagree
+
+Used by tests/test_parity_full_gpu.py (-m gpu), by bench.py (extras.parity) and by tools/parity_report.py, which
+writes profiles/r2_parity.json.  The checker is the unmodified reference compiled into oracle/_ref ("reference")
+wherever it is cheap enough (C1, the whole C2 sweep, the C3 energy balance, the C4 BRDF, a direct subsample of the
+LUTs); the 2 000-set LUT samples use the plain-C restatement, which the CPU tests pin to the reference bit for bit.
+PROSPECT-D (row a16) has no compiled reference (no Fortran compiler): its entries are marked "unpinned".
+
+Stages are compared on IDENTICAL inputs (the GPU's own LUT / spectra are handed to the checker's BRDF / energy
+code) so that every stage's error is its own; C1 and C2 are additionally compared as whole chains.
+"""
+import multiprocessing as mp
+import os
+import time
+
+import numpy as np
+
+import checkers
+from gort_b200 import workloads as wk
+
+RTOL = 1e-9
+FLOOR = 1e-12
+COND_FACTOR = 32.0
+
+_G = {}          # arrays inherited by the forked workers (set before the pool is created)
+
+
+# ---------------------------------------------------------------------------------------------------
+# summaries
+# ---------------------------------------------------------------------------------------------------
+def compare(x, ref, sens=None, band_axis=None):
+    """Summary of one output array against its reference.  band_axis: axis kept for the per-band worst case."""
+    x = np.asarray(x, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    assert x.shape == ref.shape, (x.shape, ref.shape)
+    fin_r, fin_x = np.isfinite(ref), np.isfinite(x)
+    both = fin_r & fin_x
+    # non-finite entries must coincide in position and kind (NaN with NaN, +Inf with +Inf)
+    nf_mismatch = (fin_r != fin_x) | (~fin_r & ~fin_x & ~((np.isnan(ref) & np.isnan(x)) | (ref == x)))
+    err = np.zeros(x.shape)
+    err[both] = np.abs(x[both] - ref[both])
+    rel = err / np.maximum(np.abs(np.where(both, ref, 1.0)), FLOOR)
+    beyond = both & (rel > RTOL)
+    if sens is not None:
+        s = np.asarray(sens, dtype=np.float64)
+        excused = beyond & (err <= COND_FACTOR * np.where(np.isfinite(s), s, np.inf))
+    else:
+        excused = np.zeros(x.shape, dtype=bool)
+    bad = beyond & ~excused
+    out = {
+        "n": int(x.size),
+        "max_rel_err": float(rel.max()) if x.size else 0.0,
+        "max_rel_err_not_excused": float(rel[~excused].max()) if (~excused).any() else 0.0,
+        "n_beyond_tol": int(beyond.sum()),
+        "n_excused": int(excused.sum()),
+        "worst_excused_rel": float(rel[excused].max()) if excused.any() else 0.0,
+        "n_unexplained": int(bad.sum()),
+        "worst_unexplained_rel": float(rel[bad].max()) if bad.any() else 0.0,
+        "nonfinite_ref": int((~fin_r).sum()),
+        "nonfinite_mismatch": int(nf_mismatch.sum()),
+    }
+    if band_axis is not None:
+        other = tuple(a for a in range(x.ndim) if a != band_axis % x.ndim)
+        out["per_band"] = rel.max(axis=other) if other else rel.copy()
+    return out
+
+
+def merge(a, b):
+    if a is None:
+        return b
+    out = {}
+    for k in a:
+        if k == "per_band":
+            out[k] = np.maximum(a[k], b[k])
+        elif k.startswith("max_") or k.startswith("worst_"):
+            out[k] = max(a[k], b[k])
+        else:
+            out[k] = a[k] + b[k]
+    return out
+
+
+def merge_all(dicts):
+    """list of {output name: summary} -> {output name: merged summary}"""
+    out = {}
+    for d in dicts:
+        for k, v in d.items():
+            out[k] = merge(out.get(k), v)
+    return out
+
+
+def passed(summary):
+    return summary["n_unexplained"] == 0 and summary["nonfinite_mismatch"] == 0
+
+
+def _finish(outputs, band_labels=None):
+    """numpy -> JSON: per-band vectors become lists (or 100-nm bins for the 2101-band sweep)."""
+    res = {}
+    for name, s in outputs.items():
+        s = dict(s)
+        pb = s.pop("per_band", None)
+        if pb is not None:
+            lab = (band_labels or {}).get(name)
+            if lab is not None and len(lab) == len(pb) and len(pb) > 400:
+                lab = np.asarray(lab)
+                s["worst_band"] = float(lab[int(np.argmax(pb))])
+                s["max_rel_err_per_100nm_from"] = [[int(lo), float(pb[(lab >= lo) & (lab < lo + 100)].max())]
+                                                   for lo in range(400, 2500, 100)]
+            else:
+                s["max_rel_err_per_band"] = [float(v) for v in pb]
+                if lab is not None:
+                    s["bands"] = [float(v) if not isinstance(v, str) else v for v in lab]
+        s["pass"] = passed(s)
+        res[name] = s
+    return res
+
+
+def _kind():
+    return "reference" if checkers.ref() is not None else "port"
+
+
+def _chk(kind):
+    return checkers.ref() if kind == "reference" else checkers.oracle()
+
+
+def _lut_columns(lut_gpu, lut_ref, sens):
+    """LUT record -> the four outputs of the gap-probability path, p_n0 and epgap per zenith index."""
+    s = (lambda a, b: None) if sens is None else (lambda a, b: sens[..., a:b])
+    return {
+        "lut.p_n0": compare(lut_gpu[..., 0:91], lut_ref[..., 0:91], s(0, 91), band_axis=-1),
+        "lut.epgap": compare(lut_gpu[..., 91:182], lut_ref[..., 91:182], s(91, 182), band_axis=-1),
+        "lut.k_open": compare(lut_gpu[..., 182:183], lut_ref[..., 182:183], s(182, 183)),
+        "lut.k_openep": compare(lut_gpu[..., 183:184], lut_ref[..., 183:184], s(183, 184)),
+    }
+
+
+def _lut_job(st6, lut_gpu, direct_ref=False):
+    """One LUT record against the restatement (conditioning measured only if an entry misses the tolerance)."""
+    o = checkers.oracle()
+    lut_o = o.lut(st6)
+    first = _lut_columns(lut_gpu, lut_o, None)
+    if any(v["n_beyond_tol"] for v in first.values()):
+        sens = checkers.sensitivity(lambda c: c.lut(st6), lut_o)
+        first = _lut_columns(lut_gpu, lut_o, sens)
+    if direct_ref and checkers.ref() is not None:
+        lut_r = checkers.ref().lut(st6)
+        same = bool(np.array_equal(lut_r, lut_o, equal_nan=True))
+        first["_restatement_equals_reference"] = {"n": 1, "n_equal": int(same)}
+    return first
+
+
+# ---------------------------------------------------------------------------------------------------
+# workers (module level: they run in forked processes and read the GPU results from _G)
+# ---------------------------------------------------------------------------------------------------
+def _c2_worker(job):
+    kind, lo, hi = job
+    chk = _chk(kind)
+    st, ang = _G["c2_st"], _G["c2_ang"]
+    r_ref, s_ref, k_ref = chk.brdf(st, _G["c2_lut_ref"], ang[:, lo:hi].T, *_G["c2_sp_ref"])
+    out = {"rsurf": compare(_G["c2_rsurf"][lo:hi], r_ref, band_axis=-1)}
+    # Kt = max(0, 1 - Kc - Kz - Kg) cancels: conditioning from the 1-ULP restatement (one band is enough for K)
+    sp1 = tuple(a[:1] for a in _G["c2_sp_ref"])
+    k_o = checkers.oracle().brdf(st, _G["c2_lut_ref"], ang[:, lo:hi].T, *sp1, want_scomp=False)[2]
+    ks = checkers.sensitivity(lambda c: c.brdf(st, _G["c2_lut_ref"], ang[:, lo:hi].T, *sp1, want_scomp=False)[2], k_o)
+    for j, nm in enumerate(("Kc", "Kg", "Kt", "Kz")):
+        out["kprop." + nm] = compare(_G["c2_kprop"][lo:hi, j], k_ref[:, j], ks[:, j])
+    # component signatures on the lines the GPU call was asked for (every c2_sc_step-th line)
+    step = _G["c2_sc_step"]
+    first = (-lo) % step
+    sel = np.arange(lo + first, hi, step)
+    if sel.size:
+        for j, nm in enumerate(("C", "G", "T", "Z")):
+            out["scomp." + nm] = compare(_G["c2_scomp"][sel // step, :, j], s_ref[sel - lo, :, j], band_axis=-1)
+    return out
+
+
+def _c3_worker(job):
+    kind, m = job
+    chk = _chk(kind)
+    st6 = np.ascontiguousarray(_G["c3_st"][:, m])
+    out = _lut_job(st6, _G["c3_lut"][m])
+    o = checkers.oracle()
+    rl_o, tl_o, rs_o = o.spectra(_G["c3_leaf"][:, m], _G["c3_soil"][:, m], _G["c3_wl"])
+    out["spectra.rleaf(unpinned)"] = compare(_G["c3_rl"][m], rl_o, band_axis=-1)
+    out["spectra.tleaf(unpinned)"] = compare(_G["c3_tl"][m], tl_o, band_axis=-1)
+    out["spectra.rsoil"] = compare(_G["c3_rs"][m], rs_o, band_axis=-1)
+    # energy balance on identical inputs: the GPU's own LUT record and spectra
+    args = (st6, _G["c3_lut"][m], _G["c3_ang"].T, _G["c3_rl"][m], _G["c3_tl"][m], _G["c3_rs"][m])
+    a_r, v_r, s_r = chk.energy(*args)
+    res = {"albedo": (_G["c3_alb"][m], a_r), "favegt": (_G["c3_fv"][m], v_r), "fasoil": (_G["c3_fs"][m], s_r)}
+    first = {k: compare(x, r, band_axis=-1) for k, (x, r) in res.items()}
+    if any(v["n_beyond_tol"] for v in first.values()):
+        # favegt = 1 - albedo - Fd2 + Fu2 cancels O(1) terms (gortt_albedo.c:51): measure the conditioning
+        ref_o = o.energy(*args)
+        sens = checkers.sensitivity(lambda c: c.energy(*args), ref_o)
+        first = {k: compare(res[k][0], res[k][1], sens[i], band_axis=-1) for i, k in enumerate(("albedo", "favegt", "fasoil"))}
+    out.update(first)
+    return out
+
+
+def _c4_worker(job):
+    kind, m = job
+    chk = _chk(kind)
+    st6 = np.ascontiguousarray(_G["c4_st"][:, m])
+    out = _lut_job(st6, _G["c4_lut"][m])
+    o = checkers.oracle()
+    rl_o, tl_o, rs_o = o.spectra(_G["c4_leaf"][:, m], _G["c4_soil"][:, m], _G["c4_wl"])
+    out["spectra.rleaf(unpinned)"] = compare(_G["c4_rl"][m], rl_o, band_axis=-1)
+    out["spectra.tleaf(unpinned)"] = compare(_G["c4_tl"][m], tl_o, band_axis=-1)
+    out["spectra.rsoil"] = compare(_G["c4_rs"][m], rs_o, band_axis=-1)
+    ang = np.ascontiguousarray(_G["c4_ang"][:, m, :].T)
+    args = (st6, _G["c4_lut"][m], ang, _G["c4_rl"][m], _G["c4_tl"][m], _G["c4_rs"][m])
+    r_ref, _, k_ref = chk.brdf(*args, want_scomp=False)
+    out["rsurf"] = compare(_G["c4_rsurf"][m], r_ref, band_axis=-1)
+    if "c4_kprop" in _G:
+        k_o = o.brdf(*args, want_scomp=False)[2]
+        ks = checkers.sensitivity(lambda c: c.brdf(*args, want_scomp=False)[2], k_o)
+        for j, nm in enumerate(("Kc", "Kg", "Kt", "Kz")):
+            out["kprop." + nm] = compare(_G["c4_kprop"][m][:, j], k_ref[:, j], ks[:, j])
+    return out
+
+
+def _c5_worker(job):
+    m, direct = job
+    return _lut_job(np.ascontiguousarray(_G["c5_st"][:, m]), _G["c5_lut"][m], direct_ref=direct)
+
+
+def _run(pool, fn, jobs):
+    return merge_all(pool.map(fn, jobs, chunksize=max(1, len(jobs) // (8 * (pool._processes or 1)))))
+
+
+def _pick(rng, n_total, n, forced=()):
+    n = min(n, n_total)
+    idx = rng.choice(n_total, size=n, replace=False)
+    return np.unique(np.concatenate([idx, np.asarray(list(forced), dtype=np.int64)])).astype(np.int64)
+
+
+# ---------------------------------------------------------------------------------------------------
+# the audit
+# ---------------------------------------------------------------------------------------------------
+# c2_lines 0 = the whole sweep; *_total / c5_grid shrink the workload itself (CPU self-test of this module only)
+DEFAULT_SIZES = {"c2_lines": 0, "c3_sets": 512, "c4_members": 2048, "c5_sets": 2048,
+                 "c3_total": 10000, "c4_total": 100000, "c5_grid": (8, 8, 4, 8, 8, 8)}
+BENCH_SIZES = {"c2_lines": 0, "c3_sets": 96, "c4_members": 512, "c5_sets": 512}
+
+
+def audit(gort, sizes=None, workers=None, configs=("c1", "c2", "c3", "c4", "c5"), seed=20260, log=None):
+    """Run the audit with the CUDA context `gort`; returns the JSON-ready report."""
+    sizes = dict(DEFAULT_SIZES, **(sizes or {}))
+    workers = workers or os.cpu_count() or 1
+    kind = _kind()
+    say = log or (lambda *a: None)
+    rng = np.random.Generator(np.random.PCG64(seed))
+    rep = {"tolerance": RTOL, "floor": FLOOR, "conditioning_factor": COND_FACTOR, "checker": kind,
+           "checker_note": "reference = unmodified reference C compiled into oracle/_ref; LUT samples use the plain-C "
+                           "restatement (pinned bit for bit to the reference by the CPU tests and re-checked here on a "
+                           "direct subsample); PROSPECT-D outputs are compared with the restatement only (parity unpinned)",
+           "host_workers": workers, "configs": {}}
+    t_all = time.perf_counter()
+
+    if "c1" in configs:
+        t0 = time.perf_counter()
+        chk = _chk(kind)
+        w = wk.c1_readme()
+        st = w["structure"]
+        lut = gort.lut(st)
+        rl, tl, rs = gort.spectra(w["leaf"], w["soil"], w["wavelength"])
+        rsurf, scomp, kprop = gort.brdf(st, lut, w["angles"], rl[0], tl[0], rs[0], want_scomp=True, want_kprop=True)
+        alb, fv, fs = gort.energy(st, lut, w["angles"], rl[0], tl[0], rs[0])
+        lut_r = chk.lut(st[:, 0])
+        sp_r = chk.spectra(w["leaf"][:, 0], w["soil"][:, 0], w["wavelength"])
+        r_r, s_r, k_r = chk.brdf(st[:, 0], lut_r, w["angles"].T, *sp_r)
+        a_r, v_r, f_r = chk.energy(st[:, 0], lut_r, w["angles"].T, *sp_r)
+        out = _lut_columns(lut[0], lut_r, None)
+        out.update({"spectra.rleaf(unpinned)": compare(rl[0], sp_r[0], band_axis=-1),
+                    "spectra.tleaf(unpinned)": compare(tl[0], sp_r[1], band_axis=-1),
+                    "spectra.rsoil": compare(rs[0], sp_r[2], band_axis=-1),
+                    "rsurf": compare(rsurf[0], r_r, band_axis=-1),
+                    "albedo": compare(alb[0], a_r, band_axis=-1), "favegt": compare(fv[0], v_r, band_axis=-1),
+                    "fasoil": compare(fs[0], f_r, band_axis=-1)})
+        for j, nm in enumerate(("C", "G", "T", "Z")):
+            out["scomp." + nm] = compare(scomp[0][:, :, j], s_r[:, :, j], band_axis=-1)
+        for j, nm in enumerate(("Kc", "Kg", "Kt", "Kz")):
+            out["kprop." + nm] = compare(kprop[0][:, j], k_r[:, j])
+        rep["configs"]["c1"] = {"what": "README example, whole chain (GPU LUT + spectra + BRDF + energy vs the checker's chain)",
+                                "seconds": time.perf_counter() - t0,
+                                "outputs": _finish(out, {k: w["wavelength"] for k in out})}
+        say("c1 done")
+
+    if "c2" in configs:
+        t0 = time.perf_counter()
+        chk = _chk(kind)
+        w = wk.c2_hemisphere()
+        st, ang, wl = w["structure"], w["angles"], w["wavelength"]
+        G = ang.shape[1]
+        if sizes["c2_lines"]:
+            G = min(G, int(sizes["c2_lines"]))
+            ang = np.ascontiguousarray(ang[:, :: max(1, ang.shape[1] // G)][:, :G])
+        lut = gort.lut(st)
+        rl, tl, rs = gort.spectra(w["leaf"], w["soil"], wl)
+        rsurf, kprop = gort.brdf(st, lut, ang, rl[0], tl[0], rs[0], want_kprop=True)
+        step = 4
+        _, scomp = gort.brdf(st, lut, ang[:, ::step], rl[0], tl[0], rs[0], want_scomp=True)
+        _G.update(c2_st=st[:, 0].copy(), c2_ang=ang, c2_rsurf=rsurf[0], c2_kprop=kprop[0], c2_scomp=scomp[0],
+                  c2_sc_step=step, c2_lut_ref=chk.lut(st[:, 0]),
+                  c2_sp_ref=chk.spectra(w["leaf"][:, 0], w["soil"][:, 0], wl))
+        blk = 36
+        jobs = [(kind, lo, min(G, lo + blk)) for lo in range(0, G, blk)]
+        with mp.get_context("fork").Pool(workers) as pool:
+            out = _run(pool, _c2_worker, jobs)
+        lutcmp = _lut_columns(lut[0], _G["c2_lut_ref"], None)
+        out.update(lutcmp)
+        rep["configs"]["c2"] = {"what": "hemispherical sweep, whole chain: %d lines x %d bands against the checker's own LUT, "
+                                        "spectra and BRDF; component signatures on every %dth line" % (G, wl.size, step),
+                                "lines": int(G), "bands": int(wl.size), "seconds": time.perf_counter() - t0,
+                                "outputs": _finish(out, {k: wl for k in out if k == "rsurf" or k.startswith("scomp")})}
+        for k in [k for k in _G if k.startswith("c2_")]:
+            del _G[k]
+        say("c2 done in %.1f s" % (time.perf_counter() - t0))
+
+    if "c3" in configs:
+        t0 = time.perf_counter()
+        w = wk.c3_albedo(n_sets=int(sizes["c3_total"]))
+        st, ang, wl = w["structure"], w["angles"], w["wavelength"]
+        M = st.shape[1]
+        lut = gort.lut(st)
+        rl, tl, rs = gort.spectra(w["leaf"], w["soil"], wl)
+        alb, fv, fs = gort.energy(st, lut, ang, rl, tl, rs)
+        nonfin = ~(np.isfinite(alb).all(axis=(1, 2)) & np.isfinite(fv).all(axis=(1, 2)))
+        sel = _pick(rng, M, sizes["c3_sets"], np.flatnonzero(nonfin)[:8])
+        _G.update(c3_st=st, c3_ang=ang, c3_wl=wl, c3_leaf=w["leaf"], c3_soil=w["soil"], c3_lut=lut, c3_rl=rl, c3_tl=tl,
+                  c3_rs=rs, c3_alb=alb, c3_fv=fv, c3_fs=fs)
+        with mp.get_context("fork").Pool(workers) as pool:
+            out = _run(pool, _c3_worker, [(kind, int(m)) for m in sel])
+        sun = ["sza %g" % a for a in ang[2]]
+        rep["configs"]["c3"] = {"what": "albedo / fAPAR / soil absorption, %d of %d sets x 3 sun angles x %d bands; every stage on "
+                                        "identical inputs" % (sel.size, M, wl.size),
+                                "sets_compared": int(sel.size), "sets_total": int(M), "sun_angles": sun,
+                                "sets_with_nonfinite_output": int(nonfin.sum()), "seconds": time.perf_counter() - t0,
+                                "outputs": _finish(out, {k: wl for k in ("albedo", "favegt", "fasoil", "spectra.rsoil",
+                                                                         "spectra.rleaf(unpinned)", "spectra.tleaf(unpinned)")})}
+        for k in [k for k in _G if k.startswith("c3_")]:
+            del _G[k]
+        say("c3 done in %.1f s" % (time.perf_counter() - t0))
+
+    if "c4" in configs:
+        t0 = time.perf_counter()
+        w = wk.c4_enkf(n_members=int(sizes["c4_total"]))
+        st, ang, wl = w["structure"], w["angles"], w["wavelength"]
+        M = st.shape[1]
+        lut = gort.lut(st)
+        rl, tl, rs = gort.spectra(w["leaf"], w["soil"], wl)
+        rsurf, kprop = gort.brdf(st, lut, ang, rl, tl, rs, want_kprop=True)
+        nonfin = ~np.isfinite(rsurf).all(axis=(1, 2))
+        badlut = np.isnan(lut).any(axis=1)
+        sel = _pick(rng, M, sizes["c4_members"], list(np.flatnonzero(nonfin & ~badlut)[:8]) + list(np.flatnonzero(badlut)[:4]))
+        _G.update(c4_st=st, c4_ang=ang, c4_wl=wl, c4_leaf=w["leaf"], c4_soil=w["soil"], c4_lut=lut, c4_rl=rl, c4_tl=tl,
+                  c4_rs=rs, c4_rsurf=rsurf, c4_kprop=kprop)
+        with mp.get_context("fork").Pool(workers) as pool:
+            out = _run(pool, _c4_worker, [(kind, int(m)) for m in sel])
+        rep["configs"]["c4"] = {"what": "EnKF forward operator, %d of %d members x 16 geometries x 7 MODIS bands; every stage on "
+                                        "identical inputs" % (sel.size, M),
+                                "members_compared": int(sel.size), "members_total": int(M),
+                                "members_with_nonfinite_output": int(nonfin.sum()), "members_with_nan_lut": int(badlut.sum()),
+                                "seconds": time.perf_counter() - t0,
+                                "outputs": _finish(out, {k: wl for k in ("rsurf", "spectra.rsoil", "spectra.rleaf(unpinned)",
+                                                                         "spectra.tleaf(unpinned)")})}
+        for k in [k for k in _G if k.startswith("c4_")]:
+            del _G[k]
+        say("c4 done in %.1f s" % (time.perf_counter() - t0))
+
+    if "c5" in configs:
+        t0 = time.perf_counter()
+        st = wk.c5_lut_grid(tuple(sizes["c5_grid"]))["structure"]
+        M = st.shape[1]
+        lut = gort.lut(st)
+        badlut = np.isnan(lut).any(axis=1)
+        sel = _pick(rng, M, sizes["c5_sets"], list(np.flatnonzero(badlut)[:: max(1, int(badlut.sum()) // 8)][:8]) + [0, M - 1])
+        _G.update(c5_st=st, c5_lut=lut)
+        with mp.get_context("fork").Pool(workers) as pool:
+            out = _run(pool, _c5_worker, [(int(m), bool(i % 16 == 0)) for i, m in enumerate(sel)])
+        pin = out.pop("_restatement_equals_reference", None)
+        rep["configs"]["c5"] = {"what": "KOpen / P(n) LUT records, %d of the %d grid points" % (sel.size, M),
+                                "sets_compared": int(sel.size), "sets_total": int(M), "sets_with_nan_lut": int(badlut.sum()),
+                                "restatement_vs_compiled_reference_on_this_box": pin, "seconds": time.perf_counter() - t0,
+                                "outputs": _finish(out, {"lut.p_n0": ["zenith %d" % t for t in range(91)],
+                                                         "lut.epgap": ["zenith %d" % t for t in range(91)]})}
+        for k in [k for k in _G if k.startswith("c5_")]:
+            del _G[k]
+        say("c5 done in %.1f s" % (time.perf_counter() - t0))
+
+    rep["seconds"] = time.perf_counter() - t_all
+    rep["pass"] = all(o["pass"] for c in rep["configs"].values() for o in c["outputs"].values())
+    return rep
+
+
+def headline(rep):
+    """{config: {output: [max_rel_err, n_beyond_tol, n_excused, n_unexplained]}} -- the compact table for bench lines / logs."""
+    return {c: {k: [o["max_rel_err"], o["n_beyond_tol"], o["n_excused"], o["n_unexplained"]]
+                for k, o in v["outputs"].items()} for c, v in rep["configs"].items()}
+
+
+def failures(rep):
+    return ["%s/%s: %d unexplained (worst %.3e), %d non-finite mismatches" % (c, k, o["n_unexplained"], o["worst_unexplained_rel"],
+                                                                              o["nonfinite_mismatch"])
+            for c, v in rep["configs"].items() for k, o in v["outputs"].items() if not o["pass"]]
