@@ -57,7 +57,7 @@ ABI_SYMBOLS = [
     "gort_lut_batch", "gort_lut_batch_dev", "gort_spectra_batch", "gort_spectra_batch_dev",
     "gort_prospect_batch", "gort_brdf_batch", "gort_brdf_batch_dev", "gort_energy_batch",
     "gort_energy_batch_dev", "gort_gauleg", "gort_lut_write_text", "gort_lut_read_text",
-    "gort_dfma_peak", "gort_profile_begin", "gort_profile_end",
+    "gort_dfma_peak", "gort_profile_begin", "gort_profile_end", "gort_set_overlap",
 ]
 
 
@@ -79,6 +79,7 @@ def load_library():
     lib.gort_stream.argtypes = [vp]
     lib.gort_stream.restype = vp
     lib.gort_synchronize.argtypes = [vp]
+    lib.gort_set_overlap.argtypes = [vp, C.c_int]
     lib.gort_device_count.restype = C.c_int
     lib.gort_host_alloc.argtypes = [C.c_size_t]
     lib.gort_host_alloc.restype = vp
@@ -185,6 +186,10 @@ class Gort:
 
     def synchronize(self):
         self._check(self._lib.gort_synchronize(self._h))
+
+    def set_overlap(self, enable=True):
+        """Let consecutive same-shape brdf_dev calls overlap on the GPU (contract: include/gort_b200.h)."""
+        self._check(self._lib.gort_set_overlap(self._h, int(bool(enable))))
 
     def launch_count(self):
         return self._lib.gort_launch_count(self._h)

@@ -33,11 +33,15 @@ static void *grow(gort_ctx *ctx, void **p, size_t *cap, size_t bytes)
     if (*cap >= bytes) return *p;
     // the buffer may still be in use by work enqueued earlier (on the context's stream or on a
     // caller-supplied one); regrowth is rare, so wait for the whole device
-    cudaDeviceSynchronize();
-    if (*p) cudaFree(*p);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { set_error(ctx, GORT_ERR_CUDA, "device synchronize before regrowing a buffer: %s", cudaGetErrorString(e)); return NULL; }
+    if (*p) {
+        e = cudaFree(*p);
+        if (e != cudaSuccess) { set_error(ctx, GORT_ERR_CUDA, "cudaFree while regrowing a buffer: %s", cudaGetErrorString(e)); return NULL; }
+    }
     *p = NULL; *cap = 0;
     size_t want = bytes + bytes / 8;
-    cudaError_t e = cudaMalloc(p, want);
+    e = cudaMalloc(p, want);
     if (e != cudaSuccess) { e = cudaMalloc(p, bytes); want = bytes; }
     if (e != cudaSuccess) { *p = NULL; set_error(ctx, GORT_ERR_NOMEM, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e)); return NULL; }
     *cap = want;
@@ -47,6 +51,7 @@ static void *grow(gort_ctx *ctx, void **p, size_t *cap, size_t bytes)
 void *scratch(gort_ctx *ctx, int slot, size_t bytes) { return grow(ctx, &ctx->scratch[slot], &ctx->scratch_cap[slot], bytes); }
 void *workspace(gort_ctx *ctx, size_t bytes) { return grow(ctx, &ctx->work, &ctx->work_cap, bytes); }
 void *rec_buffer(gort_ctx *ctx, int which, size_t bytes) { return grow(ctx, &ctx->rec_buf[which], &ctx->rec_cap[which], bytes); }
+void *tab_buffer(gort_ctx *ctx, int which, size_t bytes) { return grow(ctx, &ctx->tab_buf[which], &ctx->tab_cap[which], bytes); }
 
 }  // namespace gort
 
@@ -90,6 +95,16 @@ int gort_create(int device, gort_ctx **out)
         cudaMalloc((void **) &ctx->d_prospect, sizeof(double) * 9 * GORT_PROSPECT_NW) != cudaSuccess ||
         cudaMalloc((void **) &ctx->d_soil, sizeof(double) * 4 * GORT_SOIL_NW) != cudaSuccess)
         rc = set_error(ctx, GORT_ERR_NOMEM, "cudaMalloc of constant tables failed");
+    // BRDF pipeline flags: per-CTA epochs + the fault word, cleared here, before anything can poll them
+    if (rc == GORT_OK && cudaMalloc((void **) &ctx->d_done, sizeof(unsigned long long) * (GORT_MAX_WIDE_CTAS + 1)) != cudaSuccess)
+        rc = set_error(ctx, GORT_ERR_NOMEM, "cudaMalloc of the pipeline flags failed");
+    if (rc == GORT_OK) rc = check_cuda(ctx, cudaMemsetAsync(ctx->d_done, 0, sizeof(unsigned long long) * (GORT_MAX_WIDE_CTAS + 1), ctx->stream), "pipeline flags");
+    if (rc == GORT_OK) rc = check_cuda(ctx, cudaEventCreateWithFlags(&ctx->xstream_ev, cudaEventDisableTiming), "cudaEventCreate");
+    ctx->dbg_no_pdl = getenv("GORT_NO_PDL") ? 1 : 0;
+    ctx->dbg_no_tma = getenv("GORT_NO_TMA") ? 1 : 0;
+    ctx->dbg_rows_on = getenv("GORT_ROWS") ? 1 : 0;
+    ctx->dbg_rows = getenv("GORT_ROWS_DBG") ? atoi(getenv("GORT_ROWS_DBG")) : 0;
+    ctx->dbg_timeline = getenv("GORT_TIMELINE") ? atoi(getenv("GORT_TIMELINE")) : 0;
     if (rc == GORT_OK) rc = launch_gauleg(ctx, ctx->stream, ctx->d_gauleg);
     if (rc == GORT_OK) rc = launch_tav_tables(ctx, ctx->stream, ctx->d_prospect);
     if (rc == GORT_OK) rc = upload_soil_tables(ctx, ctx->stream, ctx->d_soil);
@@ -110,9 +125,13 @@ void gort_destroy(gort_ctx *ctx)
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (int i = 0; i < GORT_NSCRATCH; i++) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
     if (ctx->work) cudaFree(ctx->work);
-    for (int i = 0; i < 2; i++) if (ctx->rec_buf[i]) cudaFree(ctx->rec_buf[i]);
+    for (int i = 0; i < 2; i++) {
+        if (ctx->rec_buf[i]) cudaFree(ctx->rec_buf[i]);
+        if (ctx->tab_buf[i]) cudaFree(ctx->tab_buf[i]);
+        if (ctx->d_flags[i]) cudaFree(ctx->d_flags[i]);
+    }
     if (ctx->d_done) cudaFree(ctx->d_done);
-    if (ctx->d_tile_flags) cudaFree(ctx->d_tile_flags);
+    if (ctx->d_timeline) cudaFree(ctx->d_timeline);
     if (ctx->xstream_ev) cudaEventDestroy(ctx->xstream_ev);
     if (ctx->d_gauleg) cudaFree(ctx->d_gauleg);
     if (ctx->d_prospect) cudaFree(ctx->d_prospect);
@@ -133,7 +152,11 @@ static int check_pipeline_fault(gort_ctx *ctx)
     unsigned long long f = 0;
     cudaError_t e = cudaMemcpy(&f, ctx->d_done + GORT_MAX_WIDE_CTAS, sizeof f, cudaMemcpyDeviceToHost);
     if (e != cudaSuccess) return check_cuda(ctx, e, "pipeline fault word");
-    if (f) return set_error(ctx, GORT_ERR_CUDA, "BRDF pipeline: an in-kernel wait timed out in call %llu; results of that call are not ordered", f);
+    if (f) {
+        // reported once: clear the word so that later calls are judged on their own
+        cudaMemset(ctx->d_done + GORT_MAX_WIDE_CTAS, 0, sizeof f);
+        return set_error(ctx, GORT_ERR_CUDA, "BRDF pipeline: an in-kernel wait timed out in call %llu; the affected CTAs stored nothing for that call", f);
+    }
     return GORT_OK;
 }
 
@@ -144,7 +167,17 @@ int gort_synchronize(gort_ctx *ctx)
     // everything this context enqueued, on its own stream and on the last caller-supplied one
     TRYCUDA(ctx, cudaStreamSynchronize(ctx->stream), "synchronize");
     if (ctx->last_stream && ctx->last_stream != ctx->stream) TRYCUDA(ctx, cudaStreamSynchronize(ctx->last_stream), "synchronize");
+    ctx->last_stream = NULL;           // everything is complete: the caller may destroy its stream now
+    ctx->last_was_wide = 0;
     return check_pipeline_fault(ctx);
+}
+
+int gort_set_overlap(gort_ctx *ctx, int enable)
+{
+    if (!ctx) return GORT_ERR_INVALID;
+    ctx->overlap = enable ? 1 : 0;
+    ctx->last_was_wide = 0;
+    return GORT_OK;
 }
 
 void *gort_host_alloc(size_t bytes)
@@ -439,9 +472,10 @@ int gort_lut_read_text(const char *path, double *lut)
     if (!path || !lut) return GORT_ERR_INVALID;
     FILE *f = fopen(path, "r");
     if (!f) return GORT_ERR_IO;
-    int j;
+    int j, rows = 0;
     double x1, x2;
     while (fscanf(f, "%d %lf %lf", &j, &x1, &x2) == 3) {
+        rows++;
         if (j >= 0) {
             if (j < GORT_NTH) { lut[j] = x1; lut[GORT_NTH + j] = x2; }   /* the reference has no bound */
         } else {
@@ -450,7 +484,7 @@ int gort_lut_read_text(const char *path, double *lut)
         }
     }
     fclose(f);
-    return GORT_OK;
+    return rows > 0 ? GORT_OK : GORT_ERR_IO;      /* nothing parsable: not a LUT file */
 }
 
 }  // extern "C"

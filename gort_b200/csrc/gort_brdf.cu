@@ -17,6 +17,7 @@
 #include "gort_device.cuh"
 #include "gort_internal.h"
 #include "gort_rsurf_wide.cuh"
+#include "gort_rsurf_rows.cuh"
 
 namespace gort {
 
@@ -31,19 +32,34 @@ namespace gort {
 //   warp 3  exp terms of Kz / K'g / t0 and the mutual-shadowing beta     gortt.c:439-449, gortt_brdf.c:223-232
 //   warp 4  zenith interpolation of the LUT and the Kuusk hotspot        gortt.c:872-915, gortt_brdf.c:638-702
 #define GEOM_ROLES 5
+// The first `n_tiles` CTAs of a geometry kernel do not compute line records: they fill the (set, lambda) table the
+// full-spectrum per-wavelength kernel loads (gort_rsurf_rows.cuh) and publish one flag per tile.  n_tiles = 0: none.
+struct TableJob {
+    int n_tiles, n_wl, spectra_per_set, ncolt;
+    const double *rleaf, *tleaf, *rsoil;
+    double *table;
+    unsigned long long *flags;          // one per tile
+};
+
 __global__ void __launch_bounds__(32 * GEOM_ROLES)
 geom_kernel(int n_sets, int n_geom, int geom_per_set, gort_options opt,
             const double* __restrict__ structure, const double* __restrict__ lut,
             const double* __restrict__ angles, double* __restrict__ rec, double* __restrict__ kprop,
-            unsigned long long* __restrict__ tile_flags, unsigned long long call_no)
+            unsigned long long* __restrict__ tile_flags, unsigned long long call_no, const TableJob tj)
 {
-    // let the dependent per-wavelength kernel start its prologue (leaf terms) while this grid runs; it still
-    // waits for this grid's completion (griddepcontrol.wait) before it reads a record
+    // let the dependent per-wavelength kernel start its prologue while this grid runs: it never waits for this
+    // grid's completion, it acquires the per-tile flags published below
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if ((int) blockIdx.x < tj.n_tiles) {
+        leaf_table_tile(blockIdx.x, n_sets, tj.n_wl, tj.spectra_per_set, tj.ncolt, structure, lut, tj.rleaf, tj.tleaf,
+                        tj.rsoil, tj.table, tj.flags, call_no);
+        return;
+    }
+    const unsigned gblock = blockIdx.x - tj.n_tiles;
     __shared__ double ex[12][32];
     const long L = (long) n_sets * n_geom;
     const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
-    const long line_raw = (long) blockIdx.x * 32 + lane;
+    const long line_raw = (long) gblock * 32 + lane;
     const long line = min(line_raw, L - 1);
     const int m = (int) (line / n_geom);
     const long a = geom_per_set ? line : (line - (long) m * n_geom);
@@ -110,7 +126,7 @@ geom_kernel(int n_sets, int n_geom, int geom_per_set, gort_options opt,
     __syncwarp();
     if (lane == 0) {
         __threadfence();
-        asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(tile_flags + blockIdx.x), "l"(call_no) : "memory");
+        asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(tile_flags + gblock), "l"(call_no) : "memory");
     }
 }
 
@@ -123,11 +139,16 @@ __global__ void __launch_bounds__(128, 6)
 geom_lines_kernel(int n_sets, int n_geom, int geom_per_set, gort_options opt,
                   const double* __restrict__ structure, const double* __restrict__ lut,
                   const double* __restrict__ angles, double* __restrict__ rec, double* __restrict__ kprop,
-                  unsigned long long* __restrict__ tile_flags, unsigned long long call_no)
+                  unsigned long long* __restrict__ tile_flags, unsigned long long call_no, const TableJob tj)
 {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if ((int) blockIdx.x < tj.n_tiles) {
+        leaf_table_tile(blockIdx.x, n_sets, tj.n_wl, tj.spectra_per_set, tj.ncolt, structure, lut, tj.rleaf, tj.tleaf,
+                        tj.rsoil, tj.table, tj.flags, call_no);
+        return;
+    }
     const long L = (long) n_sets * n_geom;
-    const long line = (long) blockIdx.x * blockDim.x + threadIdx.x;
+    const long line = (long) (blockIdx.x - tj.n_tiles) * blockDim.x + threadIdx.x;
     if (line < L) {
         const int m = (int) (line / n_geom);
         const long a = geom_per_set ? line : (line - (long) m * n_geom);
@@ -189,108 +210,29 @@ rsurf_flat_kernel(int n_sets, int n_geom, int n_wl, int spectra_per_set, long pi
     if (scomp) *reinterpret_cast<double4*>(scomp + 4 * o) = make_double4(C, S.G, S.T, S.Z);
 }
 
-static unsigned long long *timeline_buffer()
+// Development aid: with GORT_TIMELINE=<call number> in the environment of gort_create, every per-wavelength CTA records
+// %globaltimer stamps at its phase boundaries; after the given call the stamps of that call and the one before it are
+// summarised on stderr.
+static unsigned long long *timeline_half(gort_ctx *ctx, unsigned long long epoch)
 {
-    static unsigned long long *d = NULL;
-    static int on = getenv("GORT_TIMELINE") ? 1 : 0;
-    if (on && !d) cudaMalloc((void **) &d, 2 * 64 * GORT_MAX_WIDE_CTAS);
-    return d;
-}
-static void timeline_report(cudaStream_t s, int ncta, int half);
-
-template <int LPT, bool SCOMP, int MINB, int TMAB>
-static int launch_wide(gort_ctx *ctx, cudaStream_t s, const gort_shape &sh, long L, const double *structure,
-                       const double *lut, const double *rec, const double *rleaf, const double *tleaf,
-                       const double *rsoil, double *rsurf, double *scomp, bool pdl, bool gate)
-{
-    // columns written per row: the spectrum, plus -- when the caller's pitch leaves room -- the padding up to
-    // the end of the row's last 128-byte line (16 doubles), so that no row ends in a partially written line
-    const long pitch_ = sh.out_pitch > 0 ? sh.out_pitch : sh.n_wl;
-    const int n_col = (int) (pitch_ % 16 == 0 ? ((long) (sh.n_wl + 15) / 16 * 16 < pitch_ ? (long) (sh.n_wl + 15) / 16 * 16 : pitch_) : sh.n_wl);
-    // wavelength chunks: as few as possible with <= WIDE_PICK_THREADS threads per CTA, lanes spread evenly
-    // block size cap: with the TMA row ring two CTAs must still fit an SM's shared memory
-    const int pick = TMAB > 0 ? WIDE_PICK_THREADS_TMA : WIDE_PICK_THREADS;
-    const int n_chunks = (n_col + LPT * pick - 1) / (LPT * pick);
-    int threads = (n_col + n_chunks * LPT - 1) / (n_chunks * LPT);
-    threads = ((threads + 31) / 32) * 32;
-    WideArgs a;
-    a.n_sets = sh.n_sets; a.n_geom = sh.n_geom; a.n_wl = sh.n_wl; a.spectra_per_set = sh.spectra_per_set;
-    a.chunk = LPT * threads;
-    a.n_col = n_col;
-    a.pdl = pdl ? 1 : 0;
-    a.pitch = sh.out_pitch > 0 ? sh.out_pitch : sh.n_wl;
-    a.structure = structure; a.lut = lut; a.rec = rec; a.rleaf = rleaf; a.tleaf = tleaf; a.rsoil = rsoil;
-    a.rsurf = rsurf; a.scomp = scomp;
-    a.done = ctx->d_done; a.fault = ctx->d_done + GORT_MAX_WIDE_CTAS;
-    a.tile_flags = ctx->d_tile_flags; a.call_no = ctx->call_no;
-    a.tl = timeline_buffer();                                           // consecutive calls stamp alternate halves (set below)
-    constexpr int STAGE = WIDE_STAGE_LINES;
-    const size_t smem = sizeof(double2) * 8 * STAGE + sizeof(unsigned) * 4
-                      + sizeof(double) * (WIDE_NLEAF + 2 * TMAB) * (size_t) a.chunk;
-    auto kern = rsurf_wide_kernel<LPT, SCOMP, MINB, TMAB>;
-    // occupancy of this (variant, block size) is looked up once per context
-    int occ = 0;
-    for (int i = 0; i < ctx->n_wide_plan; i++) {
-        auto &pl = ctx->wide_plan[i];
-        if (pl.key_lpt == LPT && pl.key_scomp == (int) SCOMP + 2 * TMAB && pl.key_minb == MINB && pl.key_threads == threads) occ = pl.occ;
-    }
-    if (occ == 0) {
-        // allow the largest chunk any block size can ask for (256 threads), so that the attribute never shrinks
-        const size_t smem_max = sizeof(double2) * 8 * STAGE + sizeof(unsigned) * 4
-                              + sizeof(double) * (WIDE_NLEAF + 2 * TMAB) * (size_t) LPT * WIDE_MAX_THREADS;
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_max);
-        if (e != cudaSuccess) return check_cuda(ctx, e, "rsurf_wide_kernel shared memory");
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem);
-        if (e != cudaSuccess || occ < 1) occ = 1;
-        if (ctx->n_wide_plan < 8) {
-            auto &pl = ctx->wide_plan[ctx->n_wide_plan++];
-            pl.key_lpt = LPT; pl.key_scomp = (int) SCOMP + 2 * TMAB; pl.key_minb = MINB; pl.key_threads = threads; pl.key_wl = sh.n_wl; pl.occ = occ;
-        }
-    }
-    // one resident wave: grid.y contiguous line ranges so that n_chunks * grid.y ~ SMs * occupancy
-    long nby = ((long) ctx->sm_count * occ) / n_chunks;
-    if (nby < 1) nby = 1;
-    if (nby > L) nby = L;
-    a.lines_per_cta = (L + nby - 1) / nby;
-    nby = (L + a.lines_per_cta - 1) / a.lines_per_cta;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned) n_chunks, (unsigned) nby);
-    cfg.blockDim = dim3((unsigned) threads);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = s;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = pdl ? 1 : 0;
-    // per-CTA gate: CTA k waits for CTA k of the previous launch when that launch had the same shape and
-    // outputs (then CTA k wrote exactly the region this CTA k is about to write, and the grid is identical
-    // because it is a function of the shape only).  launch_brdf lets a call overlap the previous one only in
-    // that case; otherwise stream order serialises the two and there is nothing to wait for.
-    a.epoch = ++ctx->epoch;
-    if (a.tl) a.tl = timeline_buffer() + (a.epoch & 1) * 8 * GORT_MAX_WIDE_CTAS;
-    a.wait_target = gate ? a.epoch - 1 : 0;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a);
-    if (a.tl) timeline_report(s, n_chunks * (int) nby, (int) (a.epoch & 1));
-    return check_cuda(ctx, e, "rsurf_wide_kernel launch");
+    if (!ctx->dbg_timeline) return NULL;
+    if (!ctx->d_timeline && cudaMalloc((void **) &ctx->d_timeline, 2 * 64 * GORT_MAX_WIDE_CTAS) != cudaSuccess) return NULL;
+    return ctx->d_timeline + (epoch & 1) * 8 * GORT_MAX_WIDE_CTAS;
 }
 
-// Development aid: GORT_TIMELINE=<call number> makes every rsurf_wide_kernel CTA record %globaltimer stamps at its
-// phase boundaries; after the given call the stamps of that call and the one before it are summarised on stderr.
-static void timeline_report(cudaStream_t s, int ncta, int half)
+static void timeline_report(gort_ctx *ctx, cudaStream_t s, int ncta, int half, const char *kernel)
 {
-    static int calls = 0;
-    static int at = getenv("GORT_TIMELINE") ? atoi(getenv("GORT_TIMELINE")) : 0;
-    if (!at || ++calls != at) return;
+    if (!ctx->dbg_timeline || ++ctx->timeline_calls != ctx->dbg_timeline) return;
     cudaStreamSynchronize(s);
     unsigned long long *h = (unsigned long long *) malloc(64 * (size_t) ncta), *prev = (unsigned long long *) malloc(64 * (size_t) ncta);
-    cudaMemcpy(h, timeline_buffer() + half * 8 * GORT_MAX_WIDE_CTAS, 64 * (size_t) ncta, cudaMemcpyDeviceToHost);
-    cudaMemcpy(prev, timeline_buffer() + (half ^ 1) * 8 * GORT_MAX_WIDE_CTAS, 64 * (size_t) ncta, cudaMemcpyDeviceToHost);
+    if (!h || !prev) { free(h); free(prev); return; }
+    cudaMemcpy(h, ctx->d_timeline + half * 8 * GORT_MAX_WIDE_CTAS, 64 * (size_t) ncta, cudaMemcpyDeviceToHost);
+    cudaMemcpy(prev, ctx->d_timeline + (half ^ 1) * 8 * GORT_MAX_WIDE_CTAS, 64 * (size_t) ncta, cudaMemcpyDeviceToHost);
     unsigned long long t0 = ~0ull;
     for (int i = 0; i < ncta; i++) if (h[i * 8] < t0) t0 = h[i * 8];
     const char *nm[6] = {"entry", "leaf table done", "geometry complete", "first sun terms", "gate passed", "end"};
-    fprintf(stderr, "rsurf_wide_kernel timeline, call %d, %d CTAs, us since the first CTA entry of this call\n", at, ncta);
-    if (prev) {
+    fprintf(stderr, "%s timeline, call %d, %d CTAs, us since the first CTA entry of this call\n", kernel, ctx->dbg_timeline, ncta);
+    {
         double mn = 1e30, mx = -1e30, sm = 0;
         for (int i = 0; i < ncta; i++) { double v = (double) ((long long) (prev[i * 8 + 5] - t0)) * 1e-3; if (v < mn) mn = v; if (v > mx) mx = v; sm += v; }
         fprintf(stderr, "  %-20s min %8.2f avg %8.2f max %8.2f\n", "previous call: end", mn, sm / ncta, mx);
@@ -306,9 +248,179 @@ static void timeline_report(cudaStream_t s, int ncta, int half)
     free(h); free(prev);
 }
 
+// what launch_brdf hands to the per-wavelength launchers
+struct BrdfPlan {
+    long L;
+    const double *rec;
+    unsigned long long *flags;      // this call's flag array: geometry tiles, then table tiles
+    bool pdl;                       // launch as a programmatic dependent of the geometry kernel
+    bool gate;                      // overlap mode: wait per CTA for the previous launch's CTA of the same index
+};
+
+template <int LPT, bool SCOMP, int MINB, int TMAB>
+static int launch_wide(gort_ctx *ctx, cudaStream_t s, const gort_shape &sh, const BrdfPlan &pl, const double *structure,
+                       const double *lut, const double *rleaf, const double *tleaf,
+                       const double *rsoil, double *rsurf, double *scomp)
+{
+    const long L = pl.L;
+    // columns written per row: the spectrum, plus -- when the caller's pitch leaves room -- the padding up to
+    // the end of the row's last 128-byte line (16 doubles), so that no row ends in a partially written line
+    const long pitch_ = sh.out_pitch > 0 ? sh.out_pitch : sh.n_wl;
+    const int n_col = (int) (pitch_ % 16 == 0 ? ((long) (sh.n_wl + 15) / 16 * 16 < pitch_ ? (long) (sh.n_wl + 15) / 16 * 16 : pitch_) : sh.n_wl);
+    // wavelength chunks: as few as possible with <= WIDE_PICK_THREADS threads per CTA, lanes spread evenly
+    // block size cap: with the TMA row ring two CTAs must still fit an SM's shared memory
+    const int pick = TMAB > 0 ? WIDE_PICK_THREADS_TMA : WIDE_PICK_THREADS;
+    const int n_chunks = (n_col + LPT * pick - 1) / (LPT * pick);
+    int threads = (n_col + n_chunks * LPT - 1) / (n_chunks * LPT);
+    threads = ((threads + 31) / 32) * 32;
+    WideArgs a;
+    a.n_sets = sh.n_sets; a.n_geom = sh.n_geom; a.n_wl = sh.n_wl; a.spectra_per_set = sh.spectra_per_set;
+    a.chunk = LPT * threads;
+    a.n_col = n_col;
+    a.pdl = pl.pdl ? 1 : 0;
+    a.pitch = pitch_;
+    a.structure = structure; a.lut = lut; a.rec = pl.rec; a.rleaf = rleaf; a.tleaf = tleaf; a.rsoil = rsoil;
+    a.rsurf = rsurf; a.scomp = scomp;
+    a.done = ctx->d_done; a.fault = ctx->d_done + GORT_MAX_WIDE_CTAS;
+    a.tile_flags = pl.flags; a.call_no = ctx->call_no;
+    constexpr int STAGE = WIDE_STAGE_LINES;
+    const size_t smem = sizeof(double2) * 8 * STAGE + sizeof(unsigned) * 4
+                      + sizeof(double) * (WIDE_NLEAF + 2 * TMAB) * (size_t) a.chunk;
+    auto kern = rsurf_wide_kernel<LPT, SCOMP, MINB, TMAB>;
+    // occupancy of this (variant, block size) is looked up once per context
+    int occ = 0;
+    for (int i = 0; i < ctx->n_wide_plan; i++) {
+        auto &wp = ctx->wide_plan[i];
+        if (wp.key_lpt == LPT && wp.key_scomp == (int) SCOMP + 2 * TMAB && wp.key_minb == MINB && wp.key_threads == threads) occ = wp.occ;
+    }
+    if (occ == 0) {
+        // allow the largest chunk any block size can ask for, so that the attribute never shrinks
+        const size_t smem_max = sizeof(double2) * 8 * STAGE + sizeof(unsigned) * 4
+                              + sizeof(double) * (WIDE_NLEAF + 2 * TMAB) * (size_t) LPT * WIDE_MAX_THREADS;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_max);
+        if (e != cudaSuccess) return check_cuda(ctx, e, "rsurf_wide_kernel shared memory");
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem);
+        if (e != cudaSuccess || occ < 1) occ = 1;
+        if (ctx->n_wide_plan < 8) {
+            auto &wp = ctx->wide_plan[ctx->n_wide_plan++];
+            wp.key_lpt = LPT; wp.key_scomp = (int) SCOMP + 2 * TMAB; wp.key_minb = MINB; wp.key_threads = threads; wp.key_wl = sh.n_wl; wp.occ = occ;
+        }
+    }
+    // one resident wave: grid.y contiguous line ranges so that n_chunks * grid.y ~ SMs * occupancy
+    long nby = ((long) ctx->sm_count * occ) / n_chunks;
+    if (nby < 1) nby = 1;
+    if (nby > L) nby = L;
+    a.lines_per_cta = (L + nby - 1) / nby;
+    nby = (L + a.lines_per_cta - 1) / a.lines_per_cta;
+    if ((long) n_chunks * nby > GORT_MAX_WIDE_CTAS) return set_error(ctx, GORT_ERR_INVALID, "gort_brdf: grid of %ld CTAs exceeds the pipeline's flag table", (long) n_chunks * nby);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned) n_chunks, (unsigned) nby);
+    cfg.blockDim = dim3((unsigned) threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pl.pdl ? 1 : 0;
+    // per-CTA gate: CTA k waits for CTA k of the previous launch when that launch had the same kernel, shape and
+    // outputs (then CTA k wrote exactly the region this CTA k is about to write, and the grid is identical because
+    // it is a function of the shape only).  launch_brdf lets a call overlap the previous one only in that case;
+    // otherwise stream order serialises the two and there is nothing to wait for.
+    a.epoch = ++ctx->epoch;
+    a.tl = timeline_half(ctx, a.epoch);
+    a.wait_target = pl.gate ? a.epoch - 1 : 0;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a);
+    if (a.tl) timeline_report(ctx, s, n_chunks * (int) nby, (int) (a.epoch & 1), "rsurf_wide_kernel");
+    return check_cuda(ctx, e, "rsurf_wide_kernel launch");
+}
+
+// ---- full-spectrum kernel (gort_rsurf_rows.cuh) -------------------------------------------------------------------
+struct RowsShape { bool ok; int n_col, ncolt, threads, tiles_per_set; size_t smem, tab_doubles; long lines_per_cta, grid; };
+
+static RowsShape rows_shape(const gort_ctx *ctx, const gort_shape &sh, long L, const double *rsurf, const double *scomp)
+{
+    RowsShape r = {};
+    const long pitch = sh.out_pitch > 0 ? sh.out_pitch : sh.n_wl;
+    // EXPERIMENTAL, off unless GORT_ROWS=1: measured on C2 the kernel is correct (same bits as the chunked kernel) but
+    // slower -- 50 us isolated against 43.6 us: with its 153 KB table a single CTA fits an SM, so nothing overlaps its
+    // start-up (table load 3.6 us) and the (sun, lambda) terms of every new run (2 us each); see DESIGN.md 4.1
+    if (scomp || !ctx->dbg_rows_on || ctx->dbg_no_tma || pitch % 16 != 0 || ((size_t) rsurf & 15) != 0) return r;
+    const long padded = (long) (sh.n_wl + 15) / 16 * 16;
+    r.n_col = (int) (padded < pitch ? padded : pitch);
+    r.threads = ((r.n_col + 3) / 4 + 31) / 32 * 32;
+    r.ncolt = 4 * r.threads;
+    if (r.threads > ROWS_MAX_THREADS || r.threads < 256) return r;      // 1024 .. 2176 columns
+    if (L < 2L * ctx->sm_count) return r;                               // few lines: the chunked kernel spreads them better
+    r.tab_doubles = (size_t) sh.n_sets * ROWS_NLEAF * r.ncolt;
+    if (r.tab_doubles * sizeof(double) > ((size_t) 1 << 30)) return r;
+    r.tiles_per_set = r.ncolt / ROWS_TAB_TILE;
+    r.smem = sizeof(double) * (size_t) (ROWS_NLEAF + ROWS_NBUF) * r.ncolt + 128 * (size_t) ROWS_STAGE_LINES + 8 * (1 + 2 * ROWS_NBUF);
+    long nct = ctx->sm_count < L ? ctx->sm_count : L;
+    r.lines_per_cta = (L + nct - 1) / nct;
+    r.grid = (L + r.lines_per_cta - 1) / r.lines_per_cta;
+    r.ok = true;
+    return r;
+}
+
+static int launch_rows(gort_ctx *ctx, cudaStream_t s, const gort_shape &sh, const BrdfPlan &pl, const RowsShape &rs,
+                       const double *lut, const double *table, long tab_flag_base, double *rsurf)
+{
+    if (!ctx->rows_attr_set) {
+        const size_t smem_max = sizeof(double) * (size_t) (ROWS_NLEAF + ROWS_NBUF) * 4 * ROWS_MAX_THREADS + 128 * (size_t) ROWS_STAGE_LINES + 8 * (1 + 2 * ROWS_NBUF);
+        cudaError_t e = cudaFuncSetAttribute(rsurf_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_max);
+        if (e != cudaSuccess) return check_cuda(ctx, e, "rsurf_rows_kernel shared memory");
+        ctx->rows_attr_set = 1;
+    }
+    RowsArgs a;
+    a.n_sets = sh.n_sets; a.n_geom = sh.n_geom; a.n_wl = sh.n_wl; a.spectra_per_set = sh.spectra_per_set;
+    a.n_col = rs.n_col; a.ncolt = rs.ncolt;
+    a.pdl = pl.pdl ? 1 : 0;
+    a.dbg = ctx->dbg_rows;
+    a.flags = pl.flags; a.tab_flag_base = tab_flag_base; a.call_no = ctx->call_no;
+    a.fault = ctx->d_done + GORT_MAX_WIDE_CTAS; a.done = ctx->d_done;
+    a.pitch = sh.out_pitch > 0 ? sh.out_pitch : sh.n_wl;
+    a.lines_per_cta = rs.lines_per_cta;
+    a.lut = lut; a.rec = pl.rec; a.table = table; a.rsurf = rsurf;
+    a.epoch = ++ctx->epoch;
+    a.tl = timeline_half(ctx, a.epoch);
+    a.wait_target = pl.gate ? a.epoch - 1 : 0;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned) rs.grid);
+    cfg.blockDim = dim3((unsigned) rs.threads + 32);      // compute warps + the store warp
+    cfg.dynamicSmemBytes = rs.smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pl.pdl ? 1 : 0;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, rsurf_rows_kernel, a);
+    if (a.tl) timeline_report(ctx, s, (int) rs.grid, (int) (a.epoch & 1), "rsurf_rows_kernel");
+    return check_cuda(ctx, e, "rsurf_rows_kernel launch");
+}
+
 static bool ranges_overlap(const void *p, const char *lo, const char *hi)
 {
     return p && lo && (const char *) p >= lo && (const char *) p < hi;
+}
+
+// grow-only flag array of one record buffer; new entries are zeroed ON THE LAUNCH STREAM, ahead of the kernels that
+// publish and poll them
+static int ensure_flags(gort_ctx *ctx, cudaStream_t s, int which, size_t n)
+{
+    if (n <= ctx->flag_cap[which]) return GORT_OK;
+    cudaError_t e = cudaDeviceSynchronize();                      // the old array may still be polled by enqueued work
+    if (e != cudaSuccess) return check_cuda(ctx, e, "pipeline flags: synchronize");
+    if (ctx->d_flags[which]) { e = cudaFree(ctx->d_flags[which]); if (e != cudaSuccess) return check_cuda(ctx, e, "pipeline flags: cudaFree"); }
+    ctx->d_flags[which] = NULL; ctx->flag_cap[which] = 0;
+    const size_t want = n + n / 4 + 1024;
+    e = cudaMalloc((void **) &ctx->d_flags[which], sizeof(unsigned long long) * want);
+    if (e != cudaSuccess) return set_error(ctx, GORT_ERR_NOMEM, "cudaMalloc of the pipeline flags failed: %s", cudaGetErrorString(e));
+    e = cudaMemsetAsync(ctx->d_flags[which], 0, sizeof(unsigned long long) * want, s);
+    if (e != cudaSuccess) return check_cuda(ctx, e, "pipeline flags: cudaMemsetAsync");
+    ctx->flag_cap[which] = want;
+    return GORT_OK;
 }
 
 int launch_brdf(gort_ctx *ctx, cudaStream_t s, const gort_shape &sh, const double *structure,
@@ -320,73 +432,71 @@ int launch_brdf(gort_ctx *ctx, cudaStream_t s, const gort_shape &sh, const doubl
     const long L = (long) sh.n_sets * sh.n_geom;
     const long pitch = sh.out_pitch > 0 ? sh.out_pitch : sh.n_wl;
     if (pitch < sh.n_wl) return set_error(ctx, GORT_ERR_INVALID, "gort_brdf: out_pitch smaller than n_wl");
-    // development switches (A/B measurements in DESIGN.md): GORT_NO_PDL runs the two kernels of a call strictly one
-    // after the other, GORT_NO_XCALL keeps the overlap inside a call but not across calls
-    static int use_pdl = getenv("GORT_NO_PDL") ? 0 : 1;
-    static int use_xcall = getenv("GORT_NO_XCALL") ? 0 : 1;
-    if (!ctx->d_done) {
-        if (cudaMalloc((void **) &ctx->d_done, sizeof(unsigned long long) * (GORT_MAX_WIDE_CTAS + 1)) != cudaSuccess)
-            return set_error(ctx, GORT_ERR_NOMEM, "cudaMalloc of the pipeline flags failed");
-        cudaMemset(ctx->d_done, 0, sizeof(unsigned long long) * (GORT_MAX_WIDE_CTAS + 1));
-        cudaEventCreateWithFlags(&ctx->xstream_ev, cudaEventDisableTiming);
-    }
-    // calls on different streams are ordered one after the other (record buffers and the counter are shared)
+    const bool use_pdl = !ctx->dbg_no_pdl;
+    // calls on different streams are ordered one after the other (record buffers and the flags are shared)
     if (ctx->last_stream && ctx->last_stream != s) {
-        cudaEventRecord(ctx->xstream_ev, ctx->last_stream);
-        cudaStreamWaitEvent(s, ctx->xstream_ev, 0);
+        cudaError_t e = cudaEventRecord(ctx->xstream_ev, ctx->last_stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(s, ctx->xstream_ev, 0);
+        if (e != cudaSuccess) return check_cuda(ctx, e, "ordering BRDF calls across streams");
         ctx->last_was_wide = 0;
     }
-    // per-tile ready flags of the geometry records
-    {
-        const size_t tiles = (size_t) ((L + 31) / 32);
-        if (tiles > ctx->tile_cap) {
-            cudaDeviceSynchronize();
-            if (ctx->d_tile_flags) cudaFree(ctx->d_tile_flags);
-            ctx->d_tile_flags = NULL; ctx->tile_cap = 0;
-            const size_t want = tiles + tiles / 4 + 1024;
-            if (cudaMalloc((void **) &ctx->d_tile_flags, sizeof(unsigned long long) * want) != cudaSuccess)
-                return set_error(ctx, GORT_ERR_NOMEM, "cudaMalloc of the tile flags failed");
-            cudaMemset(ctx->d_tile_flags, 0, sizeof(unsigned long long) * want);
-            ctx->tile_cap = want;
-        }
-        ctx->call_no++;
-    }
-    // line records are double-buffered: this call's geometry kernel may run while the previous call's
-    // per-wavelength kernel still reads its own records
+    ctx->call_no++;
+    // line records, the (set, lambda) table and the ready flags are double-buffered by call parity: this call's
+    // geometry kernel may run while the previous call's per-wavelength kernel still reads its own
     ctx->rec_idx ^= 1;
-    double *rec = (double *) rec_buffer(ctx, ctx->rec_idx, sizeof(double) * GORT_REC_STRIDE * (size_t) L);
+    const int bi = ctx->rec_idx;
+    const RowsShape rs = sh.n_wl >= 64 ? rows_shape(ctx, sh, L, rsurf, scomp) : RowsShape{};
+    const size_t geom_tiles = (size_t) ((L + 31) / 32);
+    const size_t tab_tiles = rs.ok ? (size_t) sh.n_sets * rs.tiles_per_set : 0;
+    {
+        int rc = ensure_flags(ctx, s, bi, geom_tiles + tab_tiles);
+        if (rc != GORT_OK) return rc;
+    }
+    double *rec = (double *) rec_buffer(ctx, bi, sizeof(double) * GORT_REC_STRIDE * (size_t) L);
     if (!rec) return GORT_ERR_NOMEM;
+    double *table = NULL;
+    if (rs.ok) {
+        table = (double *) tab_buffer(ctx, bi, sizeof(double) * rs.tab_doubles);
+        if (!table) return GORT_ERR_NOMEM;
+    }
     cudaEvent_t *ev = (ctx->prof_ev && ctx->prof_n < ctx->prof_cap) ? ctx->prof_ev + 3 * ctx->prof_n : NULL;
-    if (ev) cudaEventRecord(ev[0], s);
-    // Cross-call overlap: if the previous operation this context put on the stream was a per-wavelength kernel
-    // (which releases its dependents once it is past its start-up), this call's geometry kernel is launched as a
-    // programmatic dependent that never waits: it reads only this call's inputs and writes only the other record
-    // buffer and kprop.  Not done if an input of this call aliases an output of the previous call.
+    if (ev) { cudaError_t e = cudaEventRecord(ev[0], s); if (e != cudaSuccess) return check_cuda(ctx, e, "cudaEventRecord"); }
+    // Cross-call overlap (gort_set_overlap, off by default): if the previous operation this context put on the stream
+    // was a per-wavelength kernel of the same kind, shape and outputs (it releases its dependents once it is past its
+    // start-up), this call's geometry kernel is launched as a programmatic dependent that never waits: it reads only
+    // this call's inputs and writes only the other record / table / flag buffers and kprop.  Not done if an input of
+    // this call aliases an output of the previous call, or kprop aliases anything the previous call still reads or
+    // writes.  The caller's side of the contract (nothing else enqueued on the stream in between that writes an
+    // input of this call) is stated in include/gort_b200.h.
     bool alias = false;
     {
-        const void *in[6] = {structure, lut, angles, rleaf, tleaf, rsoil};
-        for (int k = 0; k < 6; k++) for (int r = 0; r < 2; r++) alias |= ranges_overlap(in[k], ctx->last_out_lo[r], ctx->last_out_hi[r]);
+        const void *in[7] = {structure, lut, angles, rleaf, tleaf, rsoil, kprop};
+        for (int k = 0; k < 7; k++) for (int r = 0; r < 3; r++) alias |= ranges_overlap(in[k], ctx->last_out_lo[r], ctx->last_out_hi[r]);
     }
-    const unsigned long long sig[6] = {(unsigned long long) sh.n_sets, (unsigned long long) sh.n_geom, (unsigned long long) sh.n_wl,
-                                       (unsigned long long) pitch, (unsigned long long) (size_t) rsurf, (unsigned long long) (size_t) scomp};
+    const unsigned long long sig[8] = {(unsigned long long) sh.n_sets, (unsigned long long) sh.n_geom, (unsigned long long) sh.n_wl,
+                                       (unsigned long long) pitch, (unsigned long long) (size_t) rsurf, (unsigned long long) (size_t) scomp,
+                                       (unsigned long long) (rs.ok ? 1 : 0), (unsigned long long) (size_t) kprop};
     bool same = ctx->last_was_wide != 0;
-    for (int k = 0; k < 6; k++) same &= sig[k] == ctx->last_sig[k];
-    for (int k = 0; k < 6; k++) ctx->last_sig[k] = sig[k];
-    const bool early_geom = use_pdl && use_xcall && !ev && same && !alias;
+    for (int k = 0; k < 8; k++) same &= sig[k] == ctx->last_sig[k];
+    for (int k = 0; k < 8; k++) ctx->last_sig[k] = sig[k];
+    const bool early_geom = ctx->overlap && use_pdl && !ev && same && !alias && sh.n_wl >= 64;
     {
-        int threads = 32 * GEOM_ROLES;
-        long blocks = (L + 31) / 32;
         // the per-wavelength kernel that follows needs a large shared-memory carve-out; an SM only changes its
         // carve-out when idle, so ask for the same one here or the dependent kernel's CTAs could not join this
         // kernel's CTAs on an SM (measured: without it they entered only as geom_kernel's CTAs left)
         if (!ctx->geom_carveout_set) {            // per device, so per context
-            cudaFuncSetAttribute(geom_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-            cudaFuncSetAttribute(geom_lines_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaError_t e = cudaFuncSetAttribute(geom_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(geom_lines_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            if (e != cudaSuccess) return check_cuda(ctx, e, "geometry kernel carve-out");
             ctx->geom_carveout_set = 1;
         }
+        TableJob tj = {};
+        if (rs.ok) {
+            tj.n_tiles = (int) tab_tiles; tj.n_wl = sh.n_wl; tj.spectra_per_set = sh.spectra_per_set; tj.ncolt = rs.ncolt;
+            tj.rleaf = rleaf; tj.tleaf = tleaf; tj.rsoil = rsoil; tj.table = table;
+            tj.flags = ctx->d_flags[bi] + geom_tiles;
+        }
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((unsigned) blocks);
-        cfg.blockDim = dim3((unsigned) threads);
         cfg.stream = s;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -397,51 +507,57 @@ int launch_brdf(gort_ctx *ctx, cudaStream_t s, const gort_shape &sh, const doubl
         const bool by_line = L >= 64L * 4 * ctx->sm_count;
         cudaError_t e;
         if (by_line) {
-            cfg.gridDim = dim3((unsigned) ((L + 127) / 128));
+            cfg.gridDim = dim3((unsigned) ((L + 127) / 128 + tab_tiles));
             cfg.blockDim = dim3(128);
             e = cudaLaunchKernelEx(&cfg, geom_lines_kernel, sh.n_sets, sh.n_geom, sh.geom_per_set, sh.opt,
-                                   structure, lut, angles, rec, kprop, ctx->d_tile_flags, ctx->call_no);
+                                   structure, lut, angles, rec, kprop, ctx->d_flags[bi], ctx->call_no, tj);
         } else {
+            cfg.gridDim = dim3((unsigned) ((L + 31) / 32 + tab_tiles));
+            cfg.blockDim = dim3(32 * GEOM_ROLES);
             e = cudaLaunchKernelEx(&cfg, geom_kernel, sh.n_sets, sh.n_geom, sh.geom_per_set, sh.opt,
-                                   structure, lut, angles, rec, kprop, ctx->d_tile_flags, ctx->call_no);
+                                   structure, lut, angles, rec, kprop, ctx->d_flags[bi], ctx->call_no, tj);
         }
         if (e != cudaSuccess) return check_cuda(ctx, e, "geom_kernel launch");
         ctx->launches++;
     }
-    if (ev) cudaEventRecord(ev[1], s);
+    if (ev) { cudaError_t e = cudaEventRecord(ev[1], s); if (e != cudaSuccess) return check_cuda(ctx, e, "cudaEventRecord"); }
     if (sh.n_wl >= 64) {
-        // wavelengths per thread: the value in {4, 3, 2} whose chunking wastes the fewest columns (ties: fewer
-        // chunks, then larger LPT).  GORT_WIDE_LPT overrides it (development only).
-        static int lpt_env = getenv("GORT_WIDE_LPT") ? atoi(getenv("GORT_WIDE_LPT")) : 0;
-        int lpt = lpt_env;
-        if (!lpt) {
-            const long pitch_ = pitch;
-            const long n_col = pitch_ % 16 == 0 ? ((long) (sh.n_wl + 15) / 16 * 16 < pitch_ ? (long) (sh.n_wl + 15) / 16 * 16 : pitch_) : sh.n_wl;
-            long best_waste = -1; int best_chunks = 0;
-            for (int cand = 4; cand >= 2; cand--) {
-                const long nc = (n_col + cand * WIDE_PICK_THREADS - 1) / (cand * WIDE_PICK_THREADS);
-                long thr = (n_col + nc * cand - 1) / (nc * cand);
-                thr = (thr + 31) / 32 * 32;
-                const long waste = nc * cand * thr - n_col;
-                if (best_waste < 0 || waste < best_waste || (waste == best_waste && nc < best_chunks)) { best_waste = waste; best_chunks = (int) nc; lpt = cand; }
-            }
-        }
-        // programmatic dependent launch: the kernel's (set, lambda) prologue overlaps geom_kernel.  Off while
-        // per-kernel events are being recorded (an event between the two launches would time the overlap)
-        const bool pdl = use_pdl && !ev;
+        // programmatic dependent launch: the kernel's prologue overlaps geom_kernel.  Off while per-kernel events
+        // are being recorded (an event between the two launches would time the overlap)
+        BrdfPlan pl;
+        pl.L = L; pl.rec = rec; pl.flags = ctx->d_flags[bi];
+        pl.pdl = use_pdl && !ev;
+        pl.gate = early_geom;
         int rc;
-#define WIDE_ARGS ctx, s, sh, L, structure, lut, rec, rleaf, tleaf, rsoil, rsurf, scomp, pdl, early_geom
-        // Output path: rows through shared memory and TMA bulk stores (3 rows per CTA barrier, LPT = 4) when the
-        // rows are 128-byte aligned -- measured 36.3 us per C2 call against 38.1 us for per-thread stores --
-        // else per-thread stores.  GORT_NO_TMA forces the latter (A/B measurements).
-        static int no_tma = getenv("GORT_NO_TMA") ? 1 : 0;
-        const bool tma = !no_tma && !lpt_env && pitch % 16 == 0 && ((size_t) rsurf & 15) == 0;
-        if (scomp) rc = launch_wide<2, true, 2, 0>(WIDE_ARGS);
-        else if (tma) rc = launch_wide<4, false, 2, WIDE_TMA_ROWS>(WIDE_ARGS);
-        else if (lpt == 4) rc = launch_wide<4, false, 2, 0>(WIDE_ARGS);
-        else if (lpt == 3) rc = launch_wide<3, false, 2, 0>(WIDE_ARGS);
-        else rc = launch_wide<2, false, 2, 0>(WIDE_ARGS);
+        if (rs.ok) {
+            // full spectrum, aligned rows: one persistent CTA per SM writes whole rows (gort_rsurf_rows.cuh)
+            rc = launch_rows(ctx, s, sh, pl, rs, lut, table, (long) geom_tiles, rsurf);
+        } else {
+            // wavelengths per thread: the value in {4, 3, 2} whose chunking wastes the fewest columns (ties: fewer
+            // chunks, then larger LPT)
+            int lpt = 4;
+            {
+                const long n_col = pitch % 16 == 0 ? ((long) (sh.n_wl + 15) / 16 * 16 < pitch ? (long) (sh.n_wl + 15) / 16 * 16 : pitch) : sh.n_wl;
+                long best_waste = -1; int best_chunks = 0;
+                for (int cand = 4; cand >= 2; cand--) {
+                    const long nc = (n_col + cand * WIDE_PICK_THREADS - 1) / (cand * WIDE_PICK_THREADS);
+                    long thr = (n_col + nc * cand - 1) / (nc * cand);
+                    thr = (thr + 31) / 32 * 32;
+                    const long waste = nc * cand * thr - n_col;
+                    if (best_waste < 0 || waste < best_waste || (waste == best_waste && nc < best_chunks)) { best_waste = waste; best_chunks = (int) nc; lpt = cand; }
+                }
+            }
+#define WIDE_ARGS ctx, s, sh, pl, structure, lut, rleaf, tleaf, rsoil, rsurf, scomp
+            // Output path: rows through shared memory and TMA bulk stores (3 rows per CTA barrier, LPT = 4) when the
+            // rows are 128-byte aligned, else per-thread stores
+            const bool tma = !ctx->dbg_no_tma && pitch % 16 == 0 && ((size_t) rsurf & 15) == 0;
+            if (scomp) rc = launch_wide<2, true, 2, 0>(WIDE_ARGS);
+            else if (tma) rc = launch_wide<4, false, 2, WIDE_TMA_ROWS>(WIDE_ARGS);
+            else if (lpt == 4) rc = launch_wide<4, false, 2, 0>(WIDE_ARGS);
+            else if (lpt == 3) rc = launch_wide<3, false, 2, 0>(WIDE_ARGS);
+            else rc = launch_wide<2, false, 2, 0>(WIDE_ARGS);
 #undef WIDE_ARGS
+        }
         if (rc != GORT_OK) return rc;
     } else {
         const int threads = 128;
@@ -451,11 +567,12 @@ int launch_brdf(gort_ctx *ctx, cudaStream_t s, const gort_shape &sh, const doubl
                                                                 structure, lut, rec, rleaf, tleaf, rsoil, rsurf, scomp);
     }
     ctx->launches++;
-    if (ev) { cudaEventRecord(ev[2], s); ctx->prof_n++; }
+    if (ev) { cudaError_t e = cudaEventRecord(ev[2], s); if (e != cudaSuccess) return check_cuda(ctx, e, "cudaEventRecord"); ctx->prof_n++; }
     ctx->last_stream = s;
     ctx->last_was_wide = (sh.n_wl >= 64) && !ev;
     ctx->last_out_lo[0] = (const char *) rsurf; ctx->last_out_hi[0] = (const char *) (rsurf + (size_t) L * pitch);
     ctx->last_out_lo[1] = (const char *) scomp; ctx->last_out_hi[1] = scomp ? (const char *) (scomp + 4 * (size_t) L * pitch) : NULL;
+    ctx->last_out_lo[2] = (const char *) kprop; ctx->last_out_hi[2] = kprop ? (const char *) (kprop + 4 * (size_t) L) : NULL;
     return check_cuda(ctx, cudaGetLastError(), "gort_brdf launch");
 }
 
@@ -649,6 +766,7 @@ int launch_energy(gort_ctx *ctx, cudaStream_t s, const gort_shape &sh, const dou
     if (sh.n_sets <= 0 || sh.n_geom <= 0 || sh.n_wl <= 0)
         return set_error(ctx, GORT_ERR_INVALID, "gort_energy: n_sets, n_geom and n_wl must be positive");
     const long L = (long) sh.n_sets * sh.n_geom;
+    note_other_work(ctx);
     double *zrec = (double *) workspace(ctx, sizeof(double) * GORT_EN_ZREC * GORT_EN_NZ * (size_t) L);
     if (!zrec) return GORT_ERR_NOMEM;
     {
@@ -716,6 +834,7 @@ __global__ void __launch_bounds__(256) dfma_kernel(double* out, int iters, doubl
 
 int launch_dfma_peak(gort_ctx *ctx, cudaStream_t s, double *tflops)
 {
+    note_other_work(ctx);
     const int blocks = ctx->sm_count * 8, threads = 256, iters = 4096;
     double *d = (double *) workspace(ctx, sizeof(double) * (size_t) blocks * threads);
     if (!d) return GORT_ERR_NOMEM;

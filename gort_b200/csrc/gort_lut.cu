@@ -561,6 +561,7 @@ kopen_kernel(int n_sets, double* __restrict__ lut)
 
 int launch_lut(gort_ctx *ctx, cudaStream_t s, int n_sets, const double *structure, int method, double *lut)
 {
+    note_other_work(ctx);
     if (method == GORT_LUT_Q08) lut_q08_kernel<<<n_sets, LUT_THREADS, 0, s>>>(n_sets, structure, lut);
     else {
         // group cap: as large as possible (phase 1 is shared by the whole group) while the batch still yields

@@ -58,7 +58,7 @@ struct WideArgs {
     int chunk;                    // wavelengths per CTA (= LPT * blockDim.x)
     unsigned long long *tl;       // optional timeline [grid][8] of %globaltimer stamps (GORT_TIMELINE, development aid)
     int pdl;                      // launched with programmatic stream serialization after geom_kernel
-    const unsigned long long *tile_flags;   // per 32-line tile: call number whose records geom_kernel has published
+    const unsigned long long *tile_flags;   // this call's flag array, per 32-line tile: call number whose records geom_kernel has published
     unsigned long long call_no;
     unsigned long long *fault;    // set to the call number if a bounded wait below ever expires
     unsigned long long *done;     // [grid size] per-CTA epoch: the last launch in which CTA k of this grid shape finished
@@ -82,6 +82,9 @@ rsurf_wide_kernel(const WideArgs a)
     unsigned* runmask = reinterpret_cast<unsigned*>(srec + 8 * STAGE);   // [STAGE / 32] run-start bits (16 bytes reserved)
     double* leaf = reinterpret_cast<double*>(runmask + 4);                 // [WIDE_NLEAF][chunk], 16-byte aligned
     double* ring = leaf + (size_t) WIDE_NLEAF * a.chunk;                              // TMAB > 0: [2 * TMAB][chunk] output rows
+    __shared__ int s_fault;       // a bounded wait expired: this CTA stores nothing more (and the host is told)
+    if (threadIdx.x == 0) s_fault = 0;
+    __syncthreads();
 
     const long L = (long) a.n_sets * a.n_geom;
     const unsigned cta = blockIdx.y * gridDim.x + blockIdx.x;
@@ -159,10 +162,11 @@ rsurf_wide_kernel(const WideArgs a)
                     if (v >= a.call_no) break;
                     __nanosleep(100);
                     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-                    if (t1 - t0 > 2000000000ull) { *a.fault = a.call_no; break; }   // 2 s: never hang; reported by gort_synchronize
+                    if (t1 - t0 > 2000000000ull) { *a.fault = a.call_no; s_fault = 1; break; }   // 2 s: never hang; reported by gort_synchronize
                 }
             }
             __syncthreads();
+            if (s_fault) break;                                   // the records never arrived: store nothing
             if (s0 == line_begin) WIDE_TL(2);                     // geometry records of the first stage ready
             const double2* g = reinterpret_cast<const double2*>(a.rec + (size_t) s0 * GORT_REC_STRIDE);
             const unsigned sbase = (unsigned) __cvta_generic_to_shared(srec);
@@ -237,13 +241,14 @@ rsurf_wide_kernel(const WideArgs a)
                         if (v >= a.wait_target) break;
                         __nanosleep(200);
                         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-                        if (t1 - t0 > 2000000000ull) { *a.fault = a.call_no; break; }   // 2 s: never hang; reported by gort_synchronize
+                        if (t1 - t0 > 2000000000ull) { *a.fault = a.call_no; s_fault = 1; break; }   // 2 s: never hang; reported by gort_synchronize
                     }
                 }
                 __syncthreads();
                 asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
                 gate_open = true;
                 WIDE_TL(4);                                                   // gate passed: first store follows
+                if (s_fault) break;                               // the region's previous owner never finished: store nothing
             }
             // ---- the run: only the view-dependent part per (line, lambda) ----
             int e = nl;                                           // first run start after line l
@@ -319,7 +324,9 @@ rsurf_wide_kernel(const WideArgs a)
                 }
             }
         }
+        if (s_fault) break;
     }
+    if (!gate_open) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     // publish: all stores of this CTA happen-before the flag (bulk stores complete, barrier, then fence + release
     // by one thread)
     if (TMAB > 0 && tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");

@@ -263,6 +263,7 @@ int launch_spectra(gort_ctx *ctx, cudaStream_t s, int n_sets, const double *leaf
                    double user_leaf, double user_soil, int n_wl, const double *wl,
                    double *rleaf, double *tleaf, double *rsoil)
 {
+    note_other_work(ctx);
     if (n_sets <= 0 || n_wl <= 0) return set_error(ctx, GORT_ERR_INVALID, "gort_spectra: n_sets and n_wl must be positive");
     if (user_leaf < 0.0 && !leaf) return set_error(ctx, GORT_ERR_INVALID, "gort_spectra: leaf parameters missing");
     if (user_soil < 0.0 && !soil) return set_error(ctx, GORT_ERR_INVALID, "gort_spectra: soil weights missing");
@@ -275,6 +276,7 @@ int launch_spectra(gort_ctx *ctx, cudaStream_t s, int n_sets, const double *leaf
 
 int launch_prospect_full(gort_ctx *ctx, cudaStream_t s, int n_sets, const double *leaf, double *refl, double *tran)
 {
+    note_other_work(ctx);
     if (n_sets <= 0 || !leaf) return set_error(ctx, GORT_ERR_INVALID, "gort_prospect: bad arguments");
     long total = (long) n_sets * NWP;
     prospect_full_kernel<<<(unsigned) ((total + 127) / 128), 128, 0, s>>>(n_sets, leaf, ctx->d_prospect, refl, tran);

@@ -23,14 +23,18 @@
  *     The reference convention (print to stderr, exit(EXIT_FAILURE)) is kept by the gortt CLI,
  *     not by the library.
  *   - There is no CPU fallback: without a CUDA device gort_create() fails.
- *   - One CUDA stream per context at a time.  Consecutive gort_brdf_batch_dev calls of the same shape into the
- *     same output buffers overlap on the GPU (the geometry kernel of call i+1 runs under the store phase of call
- *     i; the stores of call i+1 to a region start only after call i's stores to that region are complete), so
- *     their results are exactly those of running them one after the other.  The overlap is used only when no
- *     input of call i+1 lies inside an output buffer of call i; any other operation put on the stream between two
- *     calls (a copy, another kernel) orders them completely, as does switching streams.  The in-kernel waits of
- *     this pipeline are bounded (2 s); should one ever expire, gort_synchronize() and the host-pointer entry points
- *     return GORT_ERR_CUDA with the number of the affected call.
+ *   - One CUDA stream per context at a time.  By default every call is ordered on its stream like any other CUDA
+ *     work.  A caller-supplied stream must stay alive until the next call on another stream or gort_synchronize().
+ *   - gort_set_overlap(ctx, 1) (off by default) lets CONSECUTIVE gort_brdf_batch_dev calls of the same shape into the
+ *     same output buffers overlap on the GPU: the geometry kernel of call i+1 runs under the store phase of call i;
+ *     the stores of call i+1 to a region start only after call i's stores to that region are complete, so the
+ *     results are exactly those of running the calls one after the other.  The library uses the overlap only when
+ *     the previous operation THIS CONTEXT enqueued was such a call and no input (or kprop) of call i+1 lies inside an
+ *     output buffer of call i.  The caller's side of the contract: between two such calls nothing else is enqueued
+ *     on the stream that writes an input of the second call (kernels the library cannot see would otherwise be
+ *     overtaken); copies, other gort_* calls and stream switches are seen and order the calls completely.
+ *   - The in-kernel waits of the pipeline are bounded (2 s); should one ever expire, the affected CTAs store nothing
+ *     and gort_synchronize() and the host-pointer entry points return GORT_ERR_CUDA with the number of the call.
  */
 #ifndef GORT_B200_H
 #define GORT_B200_H
@@ -93,6 +97,8 @@ void gort_destroy(gort_ctx *ctx);
 const char *gort_last_error(const gort_ctx *ctx);      /* ctx may be NULL: creation errors */
 void *gort_stream(gort_ctx *ctx);                       /* the context's cudaStream_t */
 int gort_synchronize(gort_ctx *ctx);
+/* allow consecutive same-shape gort_brdf_batch_dev calls to overlap (see the conventions above); default 0 */
+int gort_set_overlap(gort_ctx *ctx, int enable);
 int gort_device_count(void);
 /* pinned host memory for fast H2D/D2H through the host-pointer entry points */
 void *gort_host_alloc(size_t bytes);

@@ -34,6 +34,9 @@ from gort_b200 import workloads as wk
 RTOL = 1e-9
 FLOOR = 1e-12
 COND_FACTOR = 32.0
+# the 1-ULP libm moves a given call with probability 1/2 per seed: the K proportions (differences of O(1) areal
+# proportions, cheap to evaluate) get enough seeds that a single critical call is all but certainly exercised
+K_SEEDS = tuple(range(1, 13))
 
 _G = {}          # arrays inherited by the forked workers (set before the pool is created)
 
@@ -173,7 +176,7 @@ def _c2_worker(job):
     # Kt = max(0, 1 - Kc - Kz - Kg) cancels: conditioning from the 1-ULP restatement (one band is enough for K)
     sp1 = tuple(a[:1] for a in _G["c2_sp_ref"])
     k_o = checkers.oracle().brdf(st, _G["c2_lut_ref"], ang[:, lo:hi].T, *sp1, want_scomp=False)[2]
-    ks = checkers.sensitivity(lambda c: c.brdf(st, _G["c2_lut_ref"], ang[:, lo:hi].T, *sp1, want_scomp=False)[2], k_o)
+    ks = checkers.sensitivity(lambda c: c.brdf(st, _G["c2_lut_ref"], ang[:, lo:hi].T, *sp1, want_scomp=False)[2], k_o, seeds=K_SEEDS)
     for j, nm in enumerate(("Kc", "Kg", "Kt", "Kz")):
         out["kprop." + nm] = compare(_G["c2_kprop"][lo:hi, j], k_ref[:, j], ks[:, j])
     # component signatures on the lines the GPU call was asked for (every c2_sc_step-th line)
@@ -225,8 +228,9 @@ def _c4_worker(job):
     r_ref, _, k_ref = chk.brdf(*args, want_scomp=False)
     out["rsurf"] = compare(_G["c4_rsurf"][m], r_ref, band_axis=-1)
     if "c4_kprop" in _G:
-        k_o = o.brdf(*args, want_scomp=False)[2]
-        ks = checkers.sensitivity(lambda c: c.brdf(*args, want_scomp=False)[2], k_o)
+        sargs = args[:3] + tuple(a[:1] for a in args[3:])          # one band is enough for the K proportions
+        k_o = o.brdf(*sargs, want_scomp=False)[2]
+        ks = checkers.sensitivity(lambda c: c.brdf(*sargs, want_scomp=False)[2], k_o, seeds=K_SEEDS)
         for j, nm in enumerate(("Kc", "Kg", "Kt", "Kz")):
             out["kprop." + nm] = compare(_G["c4_kprop"][m][:, j], k_ref[:, j], ks[:, j])
     return out

@@ -309,11 +309,60 @@ def test_c2_full_size_properties(gort, oracle):
     # call i): results must still be those of the last call
     ang2 = ang.copy(); ang2[0] = (ang2[0] + 2.5) % 85.0
     d_a1, d_a2 = t(ang), t(ang2)
-    for k in range(6):
-        gort.brdf_dev(t(st), t(lut), d_a2 if k % 2 else d_a1, t(rl[0]), t(tl[0]), t(rs[0]), outp)
-    gort.synchronize()
+    d_in = (t(st), t(lut), t(rl[0]), t(tl[0]), t(rs[0]))
     ref2 = gort.brdf(st, lut, ang2, rl[0], tl[0], rs[0])
-    assert np.array_equal(outp.cpu().numpy()[:, :, :2101], ref2)
+    gort.set_overlap(True)
+    try:
+        for k in range(6):
+            gort.brdf_dev(d_in[0], d_in[1], d_a2 if k % 2 else d_a1, d_in[2], d_in[3], d_in[4], outp)
+        gort.synchronize()
+        assert np.array_equal(outp.cpu().numpy()[:, :, :2101], ref2)
+        # the same through the chunked kernel (a dense, unaligned pitch cannot take the full-spectrum kernel)
+        for k in range(6):
+            gort.brdf_dev(d_in[0], d_in[1], d_a2 if k % 2 else d_a1, d_in[2], d_in[3], d_in[4], out)
+        gort.synchronize()
+        assert np.array_equal(out.cpu().numpy(), ref2)
+    finally:
+        gort.set_overlap(False)
+
+
+def test_overlap_mode_sees_other_gort_work_between_calls(gort):
+    """Overlap mode (gort_set_overlap): a LUT / spectra call of this context between two same-shape BRDF calls rewrites
+    inputs of the second one; the library must order the calls completely (the geometry kernel of the second
+    call must not become a programmatic dependent of kopen_kernel / spectra_kernel)."""
+    import torch
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    w = wk.c2_hemisphere(wl_step=1)
+    ang, wl = w["angles"][:, :3000], w["wavelength"]
+    G, W = ang.shape[1], wl.shape[0]
+    sts = [gort_b200.structure_from_options(lai=lai).reshape(6, 1) for lai in (1.0, 2.0, 3.0, 4.0, 5.0, 6.0)]
+    leaves = [wk.DEFAULT_LEAF.reshape(7, 1) * np.array([1, 1 + 0.2 * k, 1, 1, 1, 1, 1]).reshape(7, 1) for k in range(6)]
+    d_ang, d_wl, d_soil = t(ang), t(wl), t(wk.DEFAULT_SOIL.reshape(4, 1))
+    d_st = torch.empty((6, 1), dtype=torch.float64, device=dev)
+    d_lut = torch.empty((1, gort_b200.LUT_STRIDE), dtype=torch.float64, device=dev)
+    d_rl, d_tl, d_rs = (torch.empty((1, W), dtype=torch.float64, device=dev) for _ in range(3))
+    out = torch.empty((1, G, 2112), dtype=torch.float64, device=dev)
+    results = []
+    ts = torch.cuda.Stream(device=dev)
+    gort.set_overlap(True)
+    try:
+        with torch.cuda.stream(ts):
+            for k in range(6):
+                d_st.copy_(t(sts[k]), non_blocking=True)
+                gort.lut_dev(d_st, d_lut, stream=ts.cuda_stream)                         # rewrites the LUT the BRDF reads
+                gort.spectra_dev(t(leaves[k]), d_soil, d_wl, d_rl, d_tl, d_rs, stream=ts.cuda_stream)   # and the spectra
+                gort.brdf_dev(d_st, d_lut, d_ang, d_rl[0], d_tl[0], d_rs[0], out, stream=ts.cuda_stream)
+                results.append(out.clone())
+        ts.synchronize()
+        gort.synchronize()
+    finally:
+        gort.set_overlap(False)
+    for k in range(6):
+        lut = gort.lut(sts[k])
+        rl, tl, rs = gort.spectra(leaves[k], wk.DEFAULT_SOIL.reshape(4, 1), wl)
+        ref = gort.brdf(sts[k], lut, ang, rl[0], tl[0], rs[0])
+        assert np.array_equal(results[k].cpu().numpy()[:, :, :W], ref), "step %d" % k
 
 
 # ---------------------------------------------------------------------------------------------
