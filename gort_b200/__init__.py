@@ -4,4 +4,5 @@ The product is the C-ABI shared library `libgort_b200.so` (CUDA kernels for sm_1
 include/gort_b200.h) plus the C `gortt` command line; this package is the thin ctypes host binding.
 """
 from .api import (Gort, GortError, PinnedArray, LUT_FULL, LUT_Q08, LUT_STRIDE, NTH, PROSPECT_NW,  # noqa: F401
-                  load_library, lut_read_text, lut_write_text, structure_from_options, ABI_SYMBOLS)
+                  load_library, lut_read_text, lut_write_text, soil_table_read, structure_from_options, ABI_SYMBOLS,
+                  SOIL_TABLE_NW)

@@ -27,6 +27,7 @@ NTH = 91
 LUT_STRIDE = 2 * NTH + 2
 LUT_FULL, LUT_Q08 = 0, 1
 PROSPECT_NW = 2101
+SOIL_TABLE_NW = 2101
 
 _LIB_PATH = Path(__file__).resolve().parent / "libgort_b200.so"
 _dp = C.POINTER(C.c_double)
@@ -58,6 +59,7 @@ ABI_SYMBOLS = [
     "gort_prospect_batch", "gort_brdf_batch", "gort_brdf_batch_dev", "gort_energy_batch",
     "gort_energy_batch_dev", "gort_gauleg", "gort_lut_write_text", "gort_lut_read_text",
     "gort_dfma_peak", "gort_profile_begin", "gort_profile_end", "gort_set_overlap",
+    "gort_soil_table_read", "gort_soil_from_table", "gort_soil_from_table_dev",
 ]
 
 
@@ -80,6 +82,9 @@ def load_library():
     lib.gort_stream.restype = vp
     lib.gort_synchronize.argtypes = [vp]
     lib.gort_set_overlap.argtypes = [vp, C.c_int]
+    lib.gort_soil_table_read.argtypes = [C.c_char_p, vp, C.c_char_p, C.c_size_t]
+    lib.gort_soil_from_table.argtypes = [vp, vp, C.c_int, C.c_int, vp, vp]
+    lib.gort_soil_from_table_dev.argtypes = [vp, vp, vp, C.c_int, C.c_int, vp, vp]
     lib.gort_device_count.restype = C.c_int
     lib.gort_host_alloc.argtypes = [C.c_size_t]
     lib.gort_host_alloc.restype = vp
@@ -249,6 +254,14 @@ class Gort:
                                                  float(user_soil), W, _ptr(wl), _ptr(rl), _ptr(tl), _ptr(rs)))
         return rl, tl, rs
 
+    def soil_from_table(self, table, wavelength, n_sets=1):
+        """rsoil [M][W] from a 1-nm soil table (soil_table_read): finishes the reference's -soil_spectra."""
+        tab = _np(table, (SOIL_TABLE_NW,))
+        wl = _np(wavelength).ravel()
+        out = np.empty((n_sets, wl.shape[0]))
+        self._check(self._lib.gort_soil_from_table(self._h, _ptr(tab), n_sets, wl.shape[0], _ptr(wl), _ptr(out)))
+        return out
+
     def prospect(self, leaf):
         leaf = _np(leaf)
         M = leaf.shape[1]
@@ -380,6 +393,18 @@ def lut_read_text(path):
     if rc != 0:
         raise GortError(rc, "cannot read %s" % path)
     return rec
+
+
+def soil_table_read(path):
+    """"wavelength albedo" text file -> 1-nm table [2101] (the reference's own interpolation, gortt.c:1420-1428).
+    Raises GortError(5, <the reference's message>) on a malformed file."""
+    lib = load_library()
+    tab = np.empty(SOIL_TABLE_NW)
+    err = C.create_string_buffer(600)
+    rc = lib.gort_soil_table_read(os.fsencode(path), _ptr(tab), err, 600)
+    if rc != 0:
+        raise GortError(rc, err.value.decode())
+    return tab
 
 
 def structure_from_options(lambda_=0.405, r=0.76, b=None, h1=3.0, h2=8.5, favd=0.858,

@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <math.h>
 #include "gort_internal.h"
 #include "../data/gort_tables.h"
 
@@ -293,6 +294,70 @@ int gort_prospect_batch(gort_ctx *ctx, int n_sets, const double *leaf, double *r
     TRY(d2h(ctx, refl, d_r, n));
     TRY(d2h(ctx, tran, d_t, n));
     return check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "gort_prospect_batch");
+}
+
+// ---- soil spectrum file (finishes gortt_read_soil_lut, gortt.c:1388-1451) --------------------------------
+int gort_soil_table_read(const char *path, double *table, char *errbuf, size_t errlen)
+{
+    if (errbuf && errlen) errbuf[0] = '\0';
+    if (!path || !table) return GORT_ERR_INVALID;
+#define SOIL_FAIL(...) do { if (errbuf && errlen) snprintf(errbuf, errlen, __VA_ARGS__); if (fp) fclose(fp); free(line); return GORT_ERR_IO; } while (0)
+    char *line = NULL; size_t cap = 0;
+    FILE *fp = fopen(path, "r");
+    if (!fp) SOIL_FAIL("cannot open file: %s", path);                                            /* :1399-1402 */
+    for (int i = 0; i < GORT_SOIL_TABLE_NW; i++) table[i] = 0.0;
+    int n = 0;
+    double this_wl = 0, this_rs = 0, last_wl = 0, last_rs = 0;
+    while (getline(&line, &cap, fp) >= 0) {                                                      /* :1404 (no line-length limit here) */
+        n++;
+        if (sscanf(line, "%lf %lf", &this_wl, &this_rs) != 2)
+            SOIL_FAIL("error in soil file (%s), line %d", path, n + 1);                          /* :1407-1410, "n+1" sic */
+        if (n == 1 && this_wl > 400)
+            SOIL_FAIL("error in soil file (%s), first wavelength (%lf) should be <=400", path, this_wl);   /* :1412-1416 */
+        if (n > 1) {
+            for (int i = (int) ceil(last_wl); i <= floor(this_wl); i++) {                        /* :1420-1428 */
+                int index = i - 400;
+                if ((index >= 0) && (index <= 2100))
+                    table[index] = last_rs + (i - last_wl) / (this_wl - last_wl) * (this_rs - last_rs);
+            }
+        }
+        last_wl = this_wl;
+        last_rs = this_rs;
+    }
+    if (last_wl < 2500)
+        SOIL_FAIL("error in soil file (%s), last wavelength (%lf) should be >=2500", path, last_wl);       /* :1435-1438 */
+#undef SOIL_FAIL
+    fclose(fp);
+    free(line);
+    return GORT_OK;
+}
+
+int gort_soil_from_table_dev(gort_ctx *ctx, void *stream, const double *table, int n_sets, int n_wl,
+                             const double *wavelength, double *rsoil)
+{
+    if (!ctx) return GORT_ERR_INVALID;
+    if (!table || !wavelength || !rsoil || n_sets <= 0 || n_wl <= 0)
+        return set_error(ctx, GORT_ERR_INVALID, "gort_soil_from_table: bad arguments");
+    TRYCUDA(ctx, cudaSetDevice(ctx->device), "cudaSetDevice");
+    return launch_soil_table(ctx, pick(ctx, stream), table, n_sets, n_wl, wavelength, rsoil);
+}
+
+int gort_soil_from_table(gort_ctx *ctx, const double *table, int n_sets, int n_wl, const double *wavelength, double *rsoil)
+{
+    if (!ctx) return GORT_ERR_INVALID;
+    if (!table || !wavelength || !rsoil || n_sets <= 0 || n_wl <= 0)
+        return set_error(ctx, GORT_ERR_INVALID, "gort_soil_from_table: bad arguments");
+    for (int i = 0; i < n_wl; i++)
+        if (wavelength[i] < GORT_WL_MIN || wavelength[i] > GORT_WL_MAX)
+            return set_error(ctx, GORT_ERR_RANGE, "wavlength out of range (400-2500)");
+    TRYCUDA(ctx, cudaSetDevice(ctx->device), "cudaSetDevice");
+    double *d_tab, *d_wl, *d_rs;
+    TRY(h2d(ctx, 0, table, GORT_SOIL_TABLE_NW, &d_tab));
+    TRY(h2d(ctx, 1, wavelength, n_wl, &d_wl));
+    TRY(dout(ctx, 2, rsoil, (size_t) n_sets * n_wl, &d_rs));
+    TRY(gort_soil_from_table_dev(ctx, NULL, d_tab, n_sets, n_wl, d_wl, d_rs));
+    TRY(d2h(ctx, rsoil, d_rs, (size_t) n_sets * n_wl));
+    return check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "gort_soil_from_table");
 }
 
 // ---- BRDF / energy --------------------------------------------------------------------------------

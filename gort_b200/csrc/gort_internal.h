@@ -45,7 +45,7 @@ struct gort_ctx {
     cudaEvent_t xstream_ev;            // orders BRDF calls issued on different streams
     struct { int key_lpt, key_scomp, key_minb, key_wl, key_threads; int occ; } wide_plan[8];
     int n_wide_plan;
-    int geom_carveout_set, rows_attr_set;
+    int geom_carveout_set, rows_attr_set, lut_attr_set;
     // development switches, read once from the environment by gort_create (A/B measurements in DESIGN.md):
     // GORT_NO_PDL, GORT_NO_TMA, GORT_ROWS (experimental full-spectrum kernel), GORT_ROWS_DBG, GORT_TIMELINE=<call number>
     int dbg_no_pdl, dbg_no_tma, dbg_rows_on, dbg_timeline, dbg_rows;
@@ -79,6 +79,7 @@ int launch_lut(gort_ctx *ctx, cudaStream_t s, int n_sets, const double *structur
 int launch_spectra(gort_ctx *ctx, cudaStream_t s, int n_sets, const double *leaf, const double *soil,
                    double user_leaf, double user_soil, int n_wl, const double *wl,
                    double *rleaf, double *tleaf, double *rsoil);
+int launch_soil_table(gort_ctx *ctx, cudaStream_t s, const double *table, int n_sets, int n_wl, const double *wl, double *rsoil);
 int launch_prospect_full(gort_ctx *ctx, cudaStream_t s, int n_sets, const double *leaf, double *refl, double *tran);
 int launch_gauleg(gort_ctx *ctx, cudaStream_t s, double *d_out /*[2][32]*/);
 int launch_tav_tables(gort_ctx *ctx, cudaStream_t s, double *d_prospect);

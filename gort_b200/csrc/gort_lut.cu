@@ -248,17 +248,32 @@ __device__ double expected_single_crown_path(const Crown& c, const Ang& a, doubl
     return ES;
 }
 
-// lut_full_kernel: one CTA per GROUP of consecutive parameter sets that share (r, b, h1, h2) bit for bit
-// (capped at group_cap <= LUT_GROUP_CAP sets, chunk boundaries at multiples of the cap), one thread per zenith index t.
-//   phase 1, once per group: everything that depends on crown shape and zenith only -- the projected
-//            cross-section volumes v_g[h][t] (gortt_pn_kopen.c:24-32, :149-323), E[S] (:534-563), and for every
-//            entry height the tube-volume difference of :496 (Simpson rule, sphere/cylinder sections);
-//   phase 2, per sub-group of up to 8 members that also share the stem density: p_n0 = exp(-lv' v_g) and the
-//            crown-count loop (:489-527) once; per member only the bin attenuations exp(-s_bin tau') (favd) and the
-//            within-crown gap sums; then the trapezoid rule of gortt_calc_kopen, one warp per member.
-// Phase 1 is ~2/3 of a set's instructions, so LUT grids and ensembles that vary stem density / leaf area over
-// fixed crown shapes (BASELINE.json configs 4a and 5) pay it once per group instead of once per set.
+// lut_full_kernel: one CTA per GROUP of consecutive parameter sets that share (r, b, h1, h2) bit for bit (capped at
+// group_cap <= LUT_GROUP_CAP sets, chunk boundaries at multiples of the cap).
+//
+// Work decomposition (round 2).  The reference's nest is  zenith t (91) x entry height sp_i (13) x crown count n (30)
+// (gortt_pn_kopen.c:457-527).  Round 1 gave every zenith ONE thread that walked the 13 entry heights serially and kept
+// v_g[15], s'[13] and the 13 tube-volume differences in registers (96 registers, 3 warps per CTA, 22.7 % of the SM's
+// warp slots, FP64 pipe 45 % busy, 98 % of the EnKF member update).  Now a CTA is 96 x LUT_NK threads: lane = zenith
+// (neighbouring zeniths take the same branches of the sphere / cylinder geometry), and the entry heights -- and the
+// 14 + K distinct cross-sections of phase 1 -- are dealt round-robin to the LUT_NK thread rows; the per-zenith arrays
+// live in shared memory, so a thread carries one entry height at a time (<= 80 registers, two 384-thread CTAs per SM).
+//   phase 1, once per group: everything that depends on crown shape and zenith only -- the projected cross-section
+//            volumes v_g[h][t] (gortt_pn_kopen.c:24-32, :149-323), E[S] (:534-563), and for every entry height the
+//            tube-volume difference of :496 (Simpson rule, sphere/cylinder sections);
+//   phase 2, per sub-group of up to SUB members that also share the stem density: p_n0 = exp(-lv' v_g), then the
+//            crown-count loop (:489-527) once per entry height; per member only the within-crown gap sums.
+// The bin attenuation exp(-s_bin tau') of gortt_calc_epgap (:1110-1114) depends on (set, bin) only -- not on zenith,
+// entry height or crown count -- so it is TABULATED once per member (LUT_TAB bins, one exp each, the literal formula)
+// instead of being re-evaluated at every change of bin inside the crown-count loop (~10 exp per (zenith, entry height)
+// before: the largest single item of a set with its own crown shape).
+// Each thread row accumulates its entry heights in the reference's order and the LUT_NK partial sums are added in a fixed
+// order: the same terms as the reference's bin-by-bin sum in a different association (~1e-16 relative).
 #define LUT_GROUP_CAP 64
+#define LUT_NK 4                        // thread rows per CTA (entry heights / cross-sections dealt round-robin)
+#define LUT_CTA (LUT_THREADS * LUT_NK)
+#define LUT_TAB 512                     // tabulated bins of exp(-s_bin tau'); bins beyond use the formula directly
+#define LUT_NA 32                       // distinct cross-sections per zenith: 14 + K, K < 16
 // 1/n!, n = 0..30, each the FP64 quotient 1.0 / n! (the reference tabulates n! in gortt.c:752-754 and divides)
 __constant__ double c_inv_fact[LUT_MAXCROWNS + 1] = {
     1.0,
@@ -302,21 +317,40 @@ __device__ __forceinline__ bool same_shape(const double* __restrict__ st, size_t
 }
 
 template <int SUB>
-__global__ void __launch_bounds__(LUT_THREADS)
+struct LutSmem {
+    double hp[GORT_NLAYERS];                 // height_p
+    double zk[16];                           // crown-centre heights of the midpoint rule
+    int K;
+    double ang[4][LUT_THREADS];              // theta_p, sin, cos, tan per zenith
+    double es[LUT_THREADS];                  // E[S] per zenith
+    union {                                  // A is dead once v_g is summed (a barrier before the first use of part)
+        double A[LUT_NA][LUT_THREADS];           // distinct cross-sections
+        double part[LUT_NK][SUB][LUT_THREADS];   // partial within-crown gap sums per thread row
+    };
+    double vg[GORT_NLAYERS][LUT_THREADS];    // v_g[h][t]
+    double pn0[GORT_NLAYERS][LUT_THREADS];   // p_n0[h][t] of the current sub-group
+    double tube[LUT_NSP][LUT_THREADS];       // tube-volume difference per entry height
+    double tab[SUB][LUT_TAB];                // exp(-s_bin tau') per member of the current sub-group
+};
+
+template <int SUB>
+__global__ void __launch_bounds__(LUT_CTA, 2)
 lut_full_kernel(int n_sets, int group_cap, const double* __restrict__ structure, double* __restrict__ lut)
 {
-    __shared__ double s_hp[GORT_NLAYERS];        // height_p
+    extern __shared__ __align__(16) unsigned char lut_smem_raw[];
+    LutSmem<SUB>& sm = *reinterpret_cast<LutSmem<SUB>*>(lut_smem_raw);
     const int m0 = blockIdx.x;
     const int tid = threadIdx.x;
-    const int t = tid;                           // zenith index
+    const int t = tid % LUT_THREADS;             // zenith index (lanes of a warp: consecutive zeniths)
+    const int kk = tid / LUT_THREADS;            // thread row
     const size_t N = (size_t) n_sets;
     // group heads: a set whose crown shape differs from its predecessor's, or that sits on a chunk boundary
     if (m0 > 0 && (m0 % group_cap) != 0 && same_shape(structure, N, m0, m0 - 1)) return;
     int m1 = m0 + 1;
     while (m1 < n_sets && (m1 % group_cap) != 0 && same_shape(structure, N, m1, m1 - 1)) m1++;
-    // two instantiations share the work: SUB = 1 (94 registers) takes the groups whose members all differ in stem
-    // density -- in particular every single-set group --, SUB = LUT_SUB takes the groups that start with a
-    // sub-group (same stem density, favd varying)
+    // two instantiations share the work: SUB = 1 takes the groups whose members all differ in stem density -- in
+    // particular every single-set group --, SUB = LUT_SUB takes the groups that start with a sub-group (same stem
+    // density, favd varying)
     {
         const bool shares = (m1 - m0 >= 2) && structure[0 * N + m0] == structure[0 * N + m0 + 1];
         if ((SUB == 1) == shares) return;
@@ -341,140 +375,157 @@ lut_full_kernel(int n_sets, int group_cap, const double* __restrict__ structure,
     c.lv_p = 0.0; c.tau_p = 0.0;                 // per member, below
     if (tid < GORT_NLAYERS) {                                                    // gortt.c:778-781
         double height = z2 - dz * (double) (GORT_NLAYERS - 1 - tid);
-        s_hp[tid] = height / ellip;
+        sm.hp[tid] = height / ellip;
+    }
+    if (tid == LUT_THREADS) {
+        // crown-centre heights of the midpoint rule, gortt_pn_kopen.c:162: a running sum
+        int K = 0;
+        for (double z = c.h1_p + c.dz_p / 2.0; z <= c.h2_p && K < 16; z += c.dz_p) sm.zk[K++] = z;
+        sm.K = K;
+    }
+    const double dth = 1 * GORT_PI / 180.0;
+    if (kk == LUT_NK - 1 && t < GORT_NTH) {
+        double theta = dth * (double) t;                                         // gortt.c:783-797
+        if (theta >= GORT_PI / 2.0) theta = GORT_PI / 2.0 - 1.0 * GORT_PI / 180.0;
+        double th = atan(tan(theta) * ellip);
+        if (th >= GORT_PI / 2.0) th = GORT_PI / 2.0 - 1.0 * GORT_PI / 180.0;
+        sm.ang[0][t] = th; sm.ang[1][t] = sin(th); sm.ang[2][t] = cos(th); sm.ang[3][t] = tan(th);
     }
     __syncthreads();
-
-    const double dth = 1 * GORT_PI / 180.0;
-    double theta = 0.0, es = 0.0;
-    double vg[GORT_NLAYERS];            // v_g[h][t]
-    double s_p[LUT_NSP], tube[LUT_NSP]; // per entry height: path length to the canopy bottom, tube-volume difference
     Ang a;
     a.th = a.s = a.c = a.t = 0.0;
-    if (t < GORT_NTH) {
-        theta = dth * (double) t;                                                // gortt.c:783-797
-        if (theta >= GORT_PI / 2.0) theta = GORT_PI / 2.0 - 1.0 * GORT_PI / 180.0;
-        a.th = atan(tan(theta) * ellip);
-        if (a.th >= GORT_PI / 2.0) a.th = GORT_PI / 2.0 - 1.0 * GORT_PI / 180.0;
-        a.s = sin(a.th); a.c = cos(a.th); a.t = tan(a.th);
+    const bool live = t < GORT_NTH;               // 91 of 96 lanes
+    const bool path = t < GORT_NTH - 1;           // epgap only for t < nth - 1, gortt_pn_kopen.c:1099
+    if (live) { a.th = sm.ang[0][t]; a.s = sm.ang[1][t]; a.c = sm.ang[2][t]; a.t = sm.ang[3][t]; }
+    const int K = sm.K;
+    const bool tabulated = K >= 1 && K < 16;
+    const double hp0 = sm.hp[0];
+
+    // ---- phase 1 -----------------------------------------------------------------------------------
+    if (live) {
         // v_g[h][t], gortt_pn_kopen.c:29, :149-167: midpoint rule over the crown-centre height z of the projected
-        // cross-section of a crown centred at z seen from layer height h.  The cross-section depends on h - z
-        // only, the layer heights and the midpoints are both dz' apart, so the 15 x K evaluations take only
-        // 14 + K distinct values: each is evaluated once (at its first (h, z) pair) and the 15 sums are formed
-        // in the reference's order.  (The other pairs differ from it by the rounding of h - z, ~1e-16.)
-        {
-            double zk[16], A[32];
-            int K = 0;
-            for (double z = c.h1_p + c.dz_p / 2.0; z <= c.h2_p && K < 16; z += c.dz_p) zk[K++] = z;   // :162, running sum
-            if (K >= 1 && K < 16) {
+        // cross-section of a crown centred at z seen from layer height h.  The cross-section depends on h - z only,
+        // the layer heights and the midpoints are both dz' apart, so the 15 x K evaluations take only 14 + K distinct
+        // values: each is evaluated once (at its first (h, z) pair) and the 15 sums are formed in the reference's
+        // order.  (The other pairs differ from it by the rounding of h - z, ~1e-16.)
+        if (tabulated) {
 #pragma unroll 1
-                for (int j = 0; j < GORT_NLAYERS + K - 1; j++) {
-                    const int i = max(0, j - (K - 1)), k = i - (j - (K - 1));
-                    A[j] = cross_section(c, a, s_hp[i], zk[k]);
-                }
-#pragma unroll 1
-                for (int h = 0; h < GORT_NLAYERS; h++) {
-                    double vol = 0.0;
-                    for (int k = 0; k < K; k++) vol += A[h - k + K - 1] * (c.dz_p);
-                    vg[h] = vol;
-                }
-            } else {
-#pragma unroll 1
-                for (int h = 0; h < GORT_NLAYERS; h++) vg[h] = proj_volume(c, a, s_hp[h]);
+            for (int j = kk; j < GORT_NLAYERS + K - 1; j += LUT_NK) {
+                const int i = max(0, j - (K - 1)), k = i - (j - (K - 1));
+                sm.A[j][t] = cross_section(c, a, sm.hp[i], sm.zk[k]);
             }
-        }
-        if (t < GORT_NTH - 1) {                                                  // :1099
-            const double hp0 = s_hp[0];
-            es = expected_single_crown_path(c, a, hp0);                          // :445
+        } else {
 #pragma unroll 1
-            for (int k = 0; k < LUT_NSP; k++) {
-                const int sp_i = GORT_NLAYERS - 2 - k;                           // :457, 13 down to 1
-                const double hps = s_hp[sp_i];
-                s_p[k] = (double) (hps - hp0) / a.c;                             // :464
-                tube[k] = tube_vol(c, a, hp0, hps, c.h2_p) - tube_vol(c, a, hp0, hps, c.h1_p);   // :496
+            for (int h = kk; h < GORT_NLAYERS; h += LUT_NK) sm.vg[h][t] = proj_volume(c, a, sm.hp[h]);
+        }
+        if (path) {
+            if (kk == 0) sm.es[t] = expected_single_crown_path(c, a, hp0);      // :445
+#pragma unroll 1
+            for (int k = kk; k < LUT_NSP; k += LUT_NK) {
+                const double hps = sm.hp[GORT_NLAYERS - 2 - k];                  // :457, sp_i = 13 down to 1
+                sm.tube[k][t] = tube_vol(c, a, hp0, hps, c.h2_p) - tube_vol(c, a, hp0, hps, c.h1_p);   // :496
             }
         }
     }
+    __syncthreads();
+    if (live && tabulated) {
+#pragma unroll 1
+        for (int h = kk; h < GORT_NLAYERS; h += LUT_NK) {
+            double vol = 0.0;
+            for (int k = 0; k < K; k++) vol += sm.A[h - k + K - 1][t] * (c.dz_p);
+            sm.vg[h][t] = vol;
+        }
+    }
+    // (the barrier that publishes vg is the first one of the member loop)
 
     // ---- members of the group, in sub-groups of up to SUB consecutive members that also share the stem
     //      density: p_n0, P(n) and the bin sequence depend on lambda only, favd enters through the bin attenuation
     //      exp(-s_bin tau') alone (gortt_pn_kopen.c:1110-1114), so the crown-count loop runs once per sub-group
-    //      and only the attenuations and the sums are per member ----
+    //      and only the sums are per member ----
+    const double inv_ds = 1.0 / c.ds;
     for (int ms = m0; ms < m1;) {
         const double lambda = structure[0 * N + ms];
         int nj = 1;
         while (nj < SUB && ms + nj < m1 && structure[0 * N + ms + nj] == lambda) nj++;
         const double lv = lambda / (h2 - h1);
         const double lv_p = lv * ellip;
-        double tau[SUB], e_t[SUB], w_bin[SUB];
+        __syncthreads();                                 // vg complete; previous sub-group done with pn0 / tab / part
+        // bin attenuations of the sub-group's members: exp(-s_bin tau'), s_bin = bin * ds, tau' = k favd'  (:1110-1114)
+        for (int i = tid; i < nj * LUT_TAB; i += LUT_CTA) {
+            const int j = i / LUT_TAB, bin = i - j * LUT_TAB;
+            const double favd_p = structure[5 * N + ms + j] * ellip;
+            const double sbin = (double) bin * c.ds;
+            sm.tab[j][bin] = exp(-sbin * (0.5 * favd_p));
+        }
+        if (live) {
+#pragma unroll 1
+            for (int h = kk; h < GORT_NLAYERS; h += LUT_NK) sm.pn0[h][t] = exp(-1.0 * lv_p * sm.vg[h][t]);   // gortt_pn_kopen.c:30
+        }
+        __syncthreads();
+        double e_t[SUB], tau[SUB];
 #pragma unroll
         for (int j = 0; j < SUB; j++) {
-            const double favd = structure[5 * N + ms + (j < nj ? j : 0)];
-            const double favd_p = favd * ellip;
-            tau[j] = 0.5 * favd_p;
-            e_t[j] = 0.0; w_bin[j] = 0.0;
+            e_t[j] = 0.0;
+            tau[j] = 0.5 * (structure[5 * N + ms + (j < nj ? j : 0)] * ellip);
         }
-        double pn0_0 = 0.0;
-        if (t < GORT_NTH) {
-            double pn0_hi = exp(-1.0 * lv_p * vg[GORT_NLAYERS - 1]);             // p_n0[14][t]
-            pn0_0 = exp(-1.0 * lv_p * vg[0]);                                    // gortt_pn_kopen.c:30
-            if (t < GORT_NTH - 1) {
+        if (path) {
+            const double es = sm.es[t];
 #pragma unroll 1
-                for (int k = 0; k < LUT_NSP; k++) {
-                    const int sp_i = GORT_NLAYERS - 2 - k;
-                    const double pn0_lo = exp(-1.0 * lv_p * vg[sp_i]);
-                    const double P_s_p = pn0_hi - pn0_lo;                        // :43, :482  p_n0[sp_i+1] - p_n0[sp_i]
-                    pn0_hi = pn0_lo;
-                    const double temp1 = tube[k] * lv_p;                         // :497
-                    const double E = exp(-temp1);
-                    const double sp = s_p[k];
-                    // crown-count loop, gortt_pn_kopen.c:489-527, with its loop invariants hoisted:
-                    //   P(n) = temp1^n e^-temp1 / (n! (1 - e^-temp1))             :501-502
-                    //   s    = s' (1 - exp(-n E[S]/s'))                            :508
-                    // exp(-n x) is advanced as q^n (q = exp(-x)); because s selects a histogram bin through
-                    // (int)(s/ds + 0.5) (:134-139, :522) the literal exp is evaluated instead whenever the
-                    // product form (with s/ds as s * (1/ds)) lands within 1e-9 of a bin boundary, so the bin is
-                    // always the one the literal formula gives.
-                    const double c0 = E / (1.0 - E);
-                    const double inv_ds = 1.0 / c.ds;
-                    const double x = es / sp;
-                    const double q = exp(-x);
-                    double pw = 1.0, qn = 1.0;
-                    int last_idx = -1;
+            for (int k = kk; k < LUT_NSP; k += LUT_NK) {
+                const int sp_i = GORT_NLAYERS - 2 - k;
+                const double P_s_p = sm.pn0[sp_i + 1][t] - sm.pn0[sp_i][t];      // :43, :482
+                const double temp1 = sm.tube[k][t] * lv_p;                       // :497
+                const double E = exp(-temp1);
+                const double sp = (double) (sm.hp[sp_i] - hp0) / a.c;            // :464
+                // crown-count loop, gortt_pn_kopen.c:489-527, with its loop invariants hoisted:
+                //   P(n) = temp1^n e^-temp1 / (n! (1 - e^-temp1))             :501-502
+                //   s    = s' (1 - exp(-n E[S]/s'))                            :508
+                // exp(-n x) is advanced as q^n (q = exp(-x)); because s selects a histogram bin through
+                // (int)(s/ds + 0.5) (:134-139, :522) the literal exp is evaluated instead whenever the
+                // product form (with s/ds as s * (1/ds)) lands within 1e-9 of a bin boundary, so the bin is
+                // always the one the literal formula gives.
+                const double c0 = E / (1.0 - E);
+                const double x = es / sp;
+                const double q = exp(-x);
+                double pw = 1.0, qn = 1.0;
 #pragma unroll 1
-                    for (int n = 1; n <= LUT_MAXCROWNS; n++) {                   // :489
-                        pw *= temp1;                                             // temp1^n
-                        qn *= q;
-                        const double P_n = pw * c0 * c_inv_fact[n];
-                        double u = sp * (1.0 - qn) * inv_ds + 0.5;
-                        if (fabs(u - rint(u)) < 1e-9)
-                            u = sp * (1.0 - exp(-1.0 * (double) n * es / sp)) / c.ds + 0.5;
-                        const int idx = (int) u;
-                        // gortt_calc_epgap + gortt_calc_pgap, :1110-1114, :1138; the bin's attenuation is
-                        // re-used while consecutive crown counts fall into the same bin (s saturates at s')
-                        if (idx != last_idx) {
-                            const double sbin = (double) idx * c.ds;
+                for (int n = 1; n <= LUT_MAXCROWNS; n++) {                       // :489
+                    pw *= temp1;                                                 // temp1^n
+                    qn *= q;
+                    const double P_n = pw * c0 * c_inv_fact[n];
+                    double u = sp * (1.0 - qn) * inv_ds + 0.5;
+                    if (fabs(u - rint(u)) < 1e-9)
+                        u = sp * (1.0 - exp(-1.0 * (double) n * es / sp)) / c.ds + 0.5;
+                    const int idx = (int) u;
+                    const double wgt = P_n * P_s_p;
+                    // gortt_calc_epgap + gortt_calc_pgap, :1110-1114, :1138
+                    if (idx >= 0 && idx < LUT_TAB) {
 #pragma unroll
-                            for (int j = 0; j < SUB; j++) if (j < nj) w_bin[j] = exp(-sbin * tau[j]);
-                            last_idx = idx;
-                        }
-                        const double wgt = P_n * P_s_p;
+                        for (int j = 0; j < SUB; j++) e_t[j] += sm.tab[j][idx] * wgt;
+                    } else {
+                        const double sbin = (double) idx * c.ds;
 #pragma unroll
-                        for (int j = 0; j < SUB; j++) e_t[j] += w_bin[j] * wgt;
+                        for (int j = 0; j < SUB; j++) e_t[j] += exp(-sbin * tau[j]) * wgt;
                     }
                 }
             }
+        }
+        if (live) {
 #pragma unroll
-            for (int j = 0; j < SUB; j++) {
-                if (j < nj) {
-                    double* o = lut + (size_t) (ms + j) * GORT_LUT_STRIDE;
-                    o[t] = pn0_0;
-                    o[GORT_NTH + t] = e_t[j];
-                }
+            for (int j = 0; j < SUB; j++) sm.part[kk][j][t] = e_t[j];
+        }
+        __syncthreads();
+        // the openness factors (trapezoid rule over the 91 zeniths) are formed by kopen_kernel afterwards
+        if (live) {
+            for (int j = kk; j < nj; j += LUT_NK) {
+                double e = sm.part[0][j][t];
+#pragma unroll
+                for (int q2 = 1; q2 < LUT_NK; q2++) e += sm.part[q2][j][t];
+                double* o = lut + (size_t) (ms + j) * GORT_LUT_STRIDE;
+                o[t] = sm.pn0[0][t];
+                o[GORT_NTH + t] = e;
             }
         }
-        // the openness factors (trapezoid rule over the 91 zeniths just written) are formed by kopen_kernel: no
-        // barrier here, so a CTA's three warps -- whose zeniths differ in cost -- never wait for each other
         ms += nj;
     }
 }
@@ -569,8 +620,15 @@ int launch_lut(gort_ctx *ctx, cudaStream_t s, int n_sets, const double *structur
         int cap = n_sets / (ctx->sm_count * 12);
         if (cap < 1) cap = 1;
         if (cap > LUT_GROUP_CAP) cap = LUT_GROUP_CAP;
-        lut_full_kernel<1><<<n_sets, LUT_THREADS, 0, s>>>(n_sets, cap, structure, lut);
-        lut_full_kernel<LUT_SUB><<<n_sets, LUT_THREADS, 0, s>>>(n_sets, cap, structure, lut);
+        static_assert(sizeof(LutSmem<LUT_SUB>) <= 113 * 1024, "two LUT CTAs per SM");
+        if (!ctx->lut_attr_set) {
+            cudaError_t e = cudaFuncSetAttribute(lut_full_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LutSmem<1>));
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(lut_full_kernel<LUT_SUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LutSmem<LUT_SUB>));
+            if (e != cudaSuccess) return check_cuda(ctx, e, "lut_full_kernel shared memory");
+            ctx->lut_attr_set = 1;
+        }
+        lut_full_kernel<1><<<n_sets, LUT_CTA, sizeof(LutSmem<1>), s>>>(n_sets, cap, structure, lut);
+        lut_full_kernel<LUT_SUB><<<n_sets, LUT_CTA, sizeof(LutSmem<LUT_SUB>), s>>>(n_sets, cap, structure, lut);
         kopen_kernel<<<(unsigned) (((long) n_sets * 32 + 127) / 128), 128, 0, s>>>(n_sets, lut);
         ctx->launches += 2;
     }

@@ -247,6 +247,35 @@ int launch_tav_tables(gort_ctx *ctx, cudaStream_t s, double *d_prospect)
     return check_cuda(ctx, cudaGetLastError(), "tav_kernel launch");
 }
 
+// rsoil from a 1-nm soil table read from a file (gort_soil_table_read): the lookup the reference declares as
+// gortt_get_rsoil_lut (include/gortt.h:296) and never defines.  Same index / fraction arithmetic as gortt_price_soil
+// (gortt.c:1311-1321) with a 1-nm step; the row past 2500 nm is never read (its weight is zero).
+__global__ void __launch_bounds__(128)
+soil_table_kernel(int n_sets, int n_wl, const double* __restrict__ table, const double* __restrict__ wl,
+                  double* __restrict__ rsoil)
+{
+    long e = (long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (long) n_sets * n_wl) return;
+    const int i = (int) (e % n_wl);
+    const double wv = wl[i];
+    if (!(wv >= GORT_WL_MIN && wv <= GORT_WL_MAX)) { rsoil[e] = __longlong_as_double(0x7ff8000000000000LL); return; }
+    int upper = (int) (1. + (wv - 400) / 1.0);
+    int lower = (int) ((wv - 400) / 1.0);
+    double fraction = (double) (wv - 400.) / 1.0 - lower;
+    double rs_lower = table[lower];
+    double rs_upper = upper < GORT_SOIL_TABLE_NW ? table[upper] : 0.0;
+    rsoil[e] = rs_lower * (1 - fraction) + rs_upper * fraction;
+}
+
+int launch_soil_table(gort_ctx *ctx, cudaStream_t s, const double *table, int n_sets, int n_wl, const double *wl, double *rsoil)
+{
+    note_other_work(ctx);
+    long total = (long) n_sets * n_wl;
+    soil_table_kernel<<<(unsigned) ((total + 127) / 128), 128, 0, s>>>(n_sets, n_wl, table, wl, rsoil);
+    ctx->launches++;
+    return check_cuda(ctx, cudaGetLastError(), "soil_table_kernel launch");
+}
+
 int upload_soil_tables(gort_ctx *ctx, cudaStream_t s, double *d_soil)
 {
     static const uint64_t *src[4] = { gort_tab_soil_eof1_f64, gort_tab_soil_eof2_f64,

@@ -31,7 +31,7 @@ typedef struct {
     double lambda, r, b, h1, h2, favd;
     /* spectra, gortt.c:38-59 */
     double leaf[7], soil[4];
-    int is_user_leaf, is_user_soil, is_file_soil;
+    int is_user_leaf, is_user_soil, is_file_soil, soil_dump;
     double user_r_leaf, user_r_soil;
     char *soil_file;
     /* control, gortt.c:32-36 */
@@ -56,7 +56,8 @@ static void usage(const char *bin)
         "leaf material: -favd x  foliage volume area density,  or  -LAI x  scene leaf area index\n"
         "PROSPECT-D:    -N x  -Cab x  -Car x  -Canth x  -Cbrown x  -Cw x  -Cm x\n"
         "Price soil:    -rsl1 x  -rsl2 x  -rsl3 x  -rsl4 x\n"
-        "overrides:     -alb_leaf x (PROSPECT off)  -alb_soil x (Price off)  -soil_spectra file\n"
+        "overrides:     -alb_leaf x (PROSPECT off)  -alb_soil x (Price off)  -soil_spectra file (Price off)\n"
+        "               -soil_dump file  print the 1-nm soil table of file and exit (the reference's unfinished -soil_spectra)\n"
         "diffuse light: -diffuse x  (diffuse fraction; default cos(sza)/(cos(sza)+0.09) direct)\n"
         "gap LUT:       -W  write gap probabilities to stdout and exit;  -P file  read them back\n"
         "               -q08_pn_kopen  closed-form gap probabilities of Quaife et al. (2008)\n"
@@ -92,6 +93,7 @@ static void parse(int argc, char **argv, cli_t *c)
         else if (!strncmp(a, "-alb_leaf", 9)) { c->is_user_leaf = 1; c->user_r_leaf = ARG(); }
         else if (!strncmp(a, "-alb_soil", 9)) { c->is_user_soil = 1; c->is_file_soil = 0; c->user_r_soil = ARG(); }
         else if (!strncmp(a, "-soil_spectra", 10)) { c->is_user_soil = 0; c->is_file_soil = 1; c->soil_file = SARG(); }
+        else if (!strncmp(a, "-soil_dump", 10)) { c->is_user_soil = 0; c->is_file_soil = 1; c->soil_dump = 1; c->soil_file = SARG(); }
         else if (!strncmp(a, "-prnspec", 7)) c->prnspec = 1;
         else if (!strncmp(a, "-prnprop", 7)) c->prnprop = 1;
         else if (!strncmp(a, "-energy", 7)) c->energy = 1;
@@ -130,39 +132,25 @@ static void parse(int argc, char **argv, cli_t *c)
         c->favd = lai * 3. / (c->lambda * c->r * c->r * M_PI * c->b * 4.0);
 }
 
-/* gortt.c:1388-1451: the reference's soil-file reader is a development stub that prints the
- * interpolated table and exits with failure; kept as is. */
-static void soil_file_stub(const cli_t *c)
+/* "-soil_spectra file" (gortt.c:1056-1060, :103).  The reference's reader (gortt.c:1388-1451) is a development stub:
+ * it builds the 1-nm table, prints it and exits with failure.  Here the option is FINISHED: the table replaces the
+ * Price soil spectrum of the run (gort_soil_table_read + gort_soil_from_table, include/gort_b200.h).  "-soil_dump
+ * file" keeps what the stub does -- the table as "%d %lf" lines, then exit(EXIT_FAILURE) -- so that the table can
+ * still be compared byte for byte with the reference binary's.  Malformed files give the reference's messages. */
+static void soil_file_read(const cli_t *c, double *table)
 {
-    static double spectra[2101];
-    FILE *fp = fopen(c->soil_file, "r");
-    if (!fp) { fprintf(stderr, "gortt: cannot open file: %s\n", c->soil_file); exit(EXIT_FAILURE); }
-    char *line = NULL; size_t cap = 0;
-    int n = 0;
-    double this_wl, this_rs, last_wl = 0, last_rs = 0;
-    while (getline(&line, &cap, fp) >= 0) {
-        n++;
-        if (sscanf(line, "%lf %lf", &this_wl, &this_rs) != 2) {
-            fprintf(stderr, "gortt: error in soil file (%s), line %d\n", c->soil_file, n + 1);
-            exit(EXIT_FAILURE);
-        }
-        if (n == 1 && this_wl > 400) {
-            fprintf(stderr, "gortt: error in soil file (%s), first wavelength (%lf) should be <=400\n", c->soil_file, this_wl);
-            exit(EXIT_FAILURE);
-        }
-        if (n > 1)
-            for (int i = (int) ceil(last_wl); i <= floor(this_wl); i++) {
-                int index = i - 400;
-                if (index >= 0 && index <= 2100)
-                    spectra[index] = last_rs + (i - last_wl) / (this_wl - last_wl) * (this_rs - last_rs);
-            }
-        last_wl = this_wl; last_rs = this_rs;
-    }
-    if (last_wl < 2500) {
-        fprintf(stderr, "gortt: error in soil file (%s), last wavelength (%lf) should be >=2500\n", c->soil_file, last_wl);
+    char err[700];
+    if (gort_soil_table_read(c->soil_file, table, err, sizeof err) != GORT_OK) {
+        fprintf(stderr, "gortt: %s\n", err);
         exit(EXIT_FAILURE);
     }
-    for (int i = 0; i <= 2100; i++) printf("%d %lf\n", i + 400, spectra[i]);
+}
+
+static void soil_file_dump(const cli_t *c)
+{
+    static double table[GORT_SOIL_TABLE_NW];
+    soil_file_read(c, table);
+    for (int i = 0; i <= 2100; i++) printf("%d %lf\n", i + 400, table[i]);      /* gortt.c:1441-1442 */
     exit(EXIT_FAILURE);
 }
 
@@ -195,7 +183,11 @@ int main(int argc, char **argv)
     c.lambda = 0.405; c.r = 0.76; c.b = 3.55263 * c.r; c.h1 = 3.0; c.h2 = 8.5; c.favd = 0.858;   /* gortt.c:67-72 */
     parse(argc, argv, &c);
 
-    if (c.is_file_soil) soil_file_stub(&c);             /* gortt.c:103 */
+    static double soil_table[GORT_SOIL_TABLE_NW];
+    if (c.is_file_soil) {                               /* gortt.c:103 */
+        if (c.soil_dump) soil_file_dump(&c);
+        soil_file_read(&c, soil_table);
+    }
 
     gort_ctx *ctx = NULL;
     if (gort_create(0, &ctx) != GORT_OK) die_gort(argv[0], NULL, "cannot initialise the GPU");
@@ -261,6 +253,7 @@ int main(int argc, char **argv)
             exit(EXIT_FAILURE);
         }
         if (rc != GORT_OK) die_gort(argv[0], ctx, "spectra");
+        if (c.is_file_soil && gort_soil_from_table(ctx, soil_table, 1, nw, wl, rsoil) != GORT_OK) die_gort(argv[0], ctx, "soil spectrum");
         /* -alb_leaf / -alb_soil may be negative in the reference; the ABI uses "< 0" for "not set" */
         if (c.is_user_leaf && c.user_r_leaf < 0.0) for (int i = 0; i < nw; i++) rleaf[i] = tleaf[i] = c.user_r_leaf / 2.0;
         if (c.is_user_soil && c.user_r_soil < 0.0) for (int i = 0; i < nw; i++) rsoil[i] = c.user_r_soil;

@@ -127,6 +127,25 @@ int gort_spectra_batch_dev(gort_ctx *ctx, void *stream, int n_sets, const double
 /* the full 2101-band PROSPECT-D output of prospect_DB_ (prospect_DB.f90:72): refl, tran [M][2101] */
 int gort_prospect_batch(gort_ctx *ctx, int n_sets, const double *leaf, double *refl, double *tran);
 
+/* ---- soil spectrum from a file ("-soil_spectra file", gortt.c:1056-1060).  The reference's reader
+ *      gortt_read_soil_lut (gortt.c:1388-1451) is unfinished: it builds the 1-nm table, prints it and exits, and the
+ *      lookup gortt_get_rsoil_lut it was meant to feed is declared (include/gortt.h:296) but never defined.  These two
+ *      calls finish the feature with the documented file format (gortt.c:1377-1387).
+ *      gort_soil_table_read: text file, one "wavelength_nm albedo" pair per line, ascending, first wavelength <= 400,
+ *      last >= 2500, arbitrary sampling -> table[GORT_SOIL_TABLE_NW] on the 1-nm grid 400..2500 by the reference's own
+ *      interpolation loop (gortt.c:1420-1428).  Host-side parsing only.  On error returns GORT_ERR_IO and writes the
+ *      reference's message (without the "gortt: " prefix) into errbuf.
+ *      gort_soil_from_table[_dev]: rsoil [M][W] at arbitrary wavelengths from such a table (shared by all M sets):
+ *      linear interpolation between the two neighbouring 1-nm rows, indices and fraction formed as
+ *      gortt_price_soil forms them for its 5-nm tables (gortt.c:1311-1314: upper = 1 + (wl-400)/1, lower = (wl-400)/1,
+ *      FP64 fraction); wavelengths outside 400-2500 are GORT_ERR_RANGE (NaN from the _dev form). */
+#define GORT_SOIL_TABLE_NW 2101
+int gort_soil_table_read(const char *path, double *table, char *errbuf, size_t errlen);
+int gort_soil_from_table(gort_ctx *ctx, const double *table, int n_sets, int n_wl, const double *wavelength,
+                         double *rsoil);
+int gort_soil_from_table_dev(gort_ctx *ctx, void *stream, const double *table, int n_sets, int n_wl,
+                             const double *wavelength, double *rsoil);
+
 /* ---- BRDF: replaces the per-line block of main (gortt.c:240-295):
  *      angle normalisation, gortt_prime_theta, fd, gortt_set_zenith_dependant_probabilities,
  *      gortt_rsurf (include/gortt.h:216-219).

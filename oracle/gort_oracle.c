@@ -24,6 +24,7 @@
 #include <string.h>
 #include <stdint.h>
 #include "gort_oracle.h"
+#include <stdio.h>
 #include "../gort_b200/data/gort_tables.h"
 
 #define NTH GORT_ORACLE_NTH
@@ -825,6 +826,56 @@ int gort_oracle_spectra(const double *leaf7, const double *soil4, double user_le
             rleaf[i] = refl[lower] * (1 - fraction) + refl[upper] * fraction;
             tleaf[i] = tran[lower] * (1 - fraction) + tran[upper] * fraction;
         }
+    }
+    return 0;
+}
+
+/* ---------------------------------------------------------------------------------------
+ * Soil spectrum file: gortt_read_soil_lut, gortt.c:1388-1451 (the reference stops after building the
+ * table -- it prints it and exits; the interpolation loop :1404-1433 is what is restated here) and the
+ * lookup gortt_get_rsoil_lut (declared include/gortt.h:296, never defined) in the form DESIGN.md gives
+ * it: gortt_price_soil's index / fraction arithmetic (gortt.c:1311-1321) on the 1-nm table.
+ * Return: 0 ok, 1 cannot open, 2 unparsable line, 3 first wavelength > 400, 4 last wavelength < 2500;
+ * *where receives the line number / wavelength the reference's message would print.
+ * ------------------------------------------------------------------------------------- */
+int gort_oracle_soil_table(const char *path, double *table, double *where)
+{
+    FILE *fp;
+    char line[1000];                                             /* MAX_LINE_LEN, include/gortt.h:28 */
+    int n = 0, i, index;
+    double this_wl, this_rs, last_wl = 0, last_rs = 0;
+    for (i = 0; i <= 2100; i++) table[i] = 0.0;
+    if ((fp = fopen(path, "r")) == NULL) return 1;               /* :1399 */
+    while (fgets(line, 1000, fp) != NULL) {                      /* :1404 */
+        n++;
+        if (sscanf(line, "%lf %lf", &this_wl, &this_rs) != 2) { *where = n + 1; fclose(fp); return 2; }   /* :1407 */
+        if (n == 1 && this_wl > 400) { *where = this_wl; fclose(fp); return 3; }                          /* :1412 */
+        if (n > 1) {
+            for (i = ceil(last_wl); i <= floor(this_wl); i++) {  /* :1420 */
+                index = i - 400;
+                if ((index >= 0) && (index <= 2100))
+                    table[index] = last_rs + (i - last_wl) / (this_wl - last_wl) * (this_rs - last_rs);   /* :1425 */
+            }
+        }
+        last_wl = this_wl;
+        last_rs = this_rs;
+    }
+    fclose(fp);
+    if (last_wl < 2500) { *where = last_wl; return 4; }          /* :1435 */
+    return 0;
+}
+
+int gort_oracle_soil_lookup(const double *table, int nw, const double *wl, double *rsoil)
+{
+    for (int i = 0; i < nw; i++)
+        if (wl[i] < 400 || wl[i] > 2500) return 1;
+    for (int i = 0; i < nw; i++) {
+        int upper = 1. + (wl[i] - 400) / 1.0;
+        int lower = (wl[i] - 400) / 1.0;
+        double fraction = (double) (wl[i] - 400.) / 1.0 - lower;
+        double rs_lower = table[lower];
+        double rs_upper = upper <= 2100 ? table[upper] : 0.0;   /* zero weight at 2500 nm, as soil_eof_sum */
+        rsoil[i] = rs_lower * (1 - fraction) + rs_upper * fraction;
     }
     return 0;
 }

@@ -29,6 +29,10 @@ long gort_oracle_brdf_repeat(const double *st6, const double *lut, int ngeom, co
                              const double *rleaf, const double *tleaf, const double *rsoil,
                              int reps, double *rsurf_last);
 
+/* soil spectrum file (gortt_read_soil_lut, gortt.c:1388-1451) and the 1-nm lookup */
+int gort_oracle_soil_table(const char *path, double *table, double *where);
+int gort_oracle_soil_lookup(const double *table, int nw, const double *wl, double *rsoil);
+
 /* from prospect_d_oracle.c */
 void gort_oracle_prospect_full(const double *leaf7, double *refl2101, double *tran2101);
 double gort_oracle_tav_abs(double theta_deg, double nr);

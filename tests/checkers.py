@@ -100,6 +100,23 @@ class Checker:
         self._spectra(_p(leaf7), _p(soil4), user_leaf, user_soil, nw, _p(wl), _p(rl), _p(tl), _p(rs))
         return rl, tl, rs
 
+    def soil_table(self, path):
+        """(restatement only) -> (rc, table[2101], where): the reference's soil-file interpolation loop."""
+        fn = self.lib.gort_oracle_soil_table
+        fn.argtypes = [C.c_char_p, _dp, _dp]
+        tab = np.empty(2101); where = np.zeros(1)
+        rc = fn(os.fsencode(str(path)), _p(tab), _p(where))
+        return rc, tab, float(where[0])
+
+    def soil_lookup(self, table, wl):
+        fn = self.lib.gort_oracle_soil_lookup
+        fn.argtypes = [_dp, C.c_int, _dp, _dp]
+        wl = np.ascontiguousarray(wl, dtype=np.float64)
+        out = np.empty(wl.shape[0])
+        rc = fn(_p(np.ascontiguousarray(table, dtype=np.float64)), wl.shape[0], _p(wl), _p(out))
+        assert rc == 0
+        return out
+
     def gauleg(self, n=32):
         x = np.empty(n); w = np.empty(n)
         self._gauleg(n, _p(x), _p(w))

@@ -6,6 +6,7 @@ Run in the build container only (needs /root/reference to have been compiled by 
 Outputs (committed, small):
     tests/golden/cli_cases.json     command lines + stdin -> exact stdout / stderr / exit code of the
                                     reference binary oracle/_ref/gortt_ref
+    tests/golden/soil_cases.json    soil-spectrum files -> the 1-nm table the reference binary prints for them
     tests/golden/ref_vectors.npz    in-memory doubles from oracle/_ref/libgortt_ref.so (LUTs, BRDF, energy,
                                     spectra) on seeded inputs
 The reference ships no golden vectors of its own; these pin the oracle restatement and
@@ -74,6 +75,41 @@ def cli_cases():
     (HERE / "cli_cases.json").write_text(json.dumps(out, indent=1))
 
 
+def soil_files():
+    """name -> text of the soil-spectrum files of the soil cases (deterministic)."""
+    rng = np.random.Generator(np.random.PCG64(77))
+    f = {}
+    wl = np.arange(350.0, 2600.1, 5.0)
+    f["grid5"] = "".join("%g %.6f\n" % (w, 0.08 + 0.25 * (1 - np.exp(-(w - 350) / 600.0)) + 0.02 * np.sin(w / 90.0)) for w in wl)
+    w = np.sort(np.concatenate([[399.3, 2500.7], rng.uniform(400, 2500, 300)]))
+    f["irregular"] = "".join("%.4f %.7f\n" % (a, b) for a, b in zip(w, 0.05 + 0.3 * rng.uniform(0, 1, w.size)))
+    f["exact1nm"] = "".join("%d %.5f\n" % (a, 0.1 + 0.0001 * (a - 400)) for a in range(400, 2501))
+    f["sparse3"] = "400 0.1\n1000 0.35\n2500 0.2\n"
+    f["wide_margins"] = "100 0.5\n399.5 0.1\n400.5 0.2\n2499.5 0.3\n3000 0.9\n"
+    f["err_first"] = "401 0.1\n2500 0.2\n"
+    f["err_last"] = "400 0.1\n2499 0.2\n"
+    f["err_line"] = "400 0.1\n1000 oops\n2500 0.2\n"
+    return f
+
+
+def soil_cases():
+    """The reference's unfinished -soil_spectra prints the interpolated 1-nm table and exits (gortt.c:1441-1442):
+    stdout / stderr / exit code of the reference binary for each soil file, run with the file in the working directory
+    (the messages quote the path as given)."""
+    import tempfile
+    out = []
+    with tempfile.TemporaryDirectory() as tmp:
+        for name, text in soil_files().items():
+            (Path(tmp) / "soil.txt").write_text(text)
+            r = subprocess.run(["gortt", "-soil_spectra", "soil.txt"], executable=str(REF_BIN), input="", capture_output=True,
+                               text=True, cwd=tmp)
+            out.append(dict(name=name, file=text, stdout=r.stdout, stderr=r.stderr, rc=r.returncode))
+            print("soil %-14s rc=%d stdout=%dB stderr=%r" % (name, r.returncode, len(r.stdout), r.stderr[:80]))
+        r = subprocess.run(["gortt", "-soil_spectra", "missing.txt"], executable=str(REF_BIN), input="", capture_output=True, text=True, cwd=tmp)
+        out.append(dict(name="err_missing", file=None, stdout=r.stdout, stderr=r.stderr, rc=r.returncode))
+    (HERE / "soil_cases.json").write_text(json.dumps(out, indent=0))
+
+
 def vectors():
     r = ref()
     rng = np.random.Generator(np.random.PCG64(2026))
@@ -115,5 +151,10 @@ def vectors():
 if __name__ == "__main__":
     if ref() is None or not REF_BIN.exists():
         raise SystemExit("oracle/_ref is not built: run `make -C oracle` where /root/reference exists")
-    cli_cases()
-    vectors()
+    only = sys.argv[1:]
+    if not only or "cli" in only:
+        cli_cases()
+    if not only or "soil" in only:
+        soil_cases()
+    if not only or "vectors" in only:
+        vectors()
