@@ -93,17 +93,38 @@ __device__ __noinline__ double proj_volume(const Crown& c, const Ang& a, double 
     return vol;
 }
 
-// gortt_pn_kopen.c:858-872
+// sqrt for the Simpson integrand (the call site was 18 % of the LUT path's instructions): MUFU.RSQ64H seed (2^-22) and
+// ONE coupled third-order Newton step on the reciprocal root, y (1 + e/2 + 3 e^2/8) with e = 1 - x y^2: the remaining
+// error is O(e^3) ~ 2^-66, so x * y is the root to within 2 ULP.  CUDA's IEEE sqrt adds a correction step, a range
+// check, a slow-path call and a reconvergence barrier (17 SASS instructions against 7); the integrand feeds a 41-point
+// quadrature whose result weights the crown-count terms smoothly, so 2 ULP here move epgap by ~1e-16.
+// Valid for x == 0 and normal x well inside the exponent range (here 0 or [1e-10, r^2]); negative x gives NaN.
+__device__ __forceinline__ double sqrt_lite(double x)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double e = fma(x, -(y * y), 1.0);
+    const double y1 = fma(fma(e, 0.375, 0.5), y * e, y);
+    return x == 0.0 ? 0.0 : x * y1;
+}
+
+// gortt_pn_kopen.c:858-872, as the reference writes it (used for the two end points)
 __device__ __forceinline__ double triang_fcn(double x, double b, double r, double tan_the)
 {
     double a1 = tan_the * (x - b);
     double a2 = r * r - x * x;
     double a3 = a2 - a1 * a1;
     if (fabs(a3) < 0.0000000001) a3 = 0.0;
-    return 2.0 * a1 * sqrt(a3);
+    return 2.0 * a1 * sqrt_lite(a3);
 }
 
-// gortt_pn_kopen.c:811-854
+// gortt_pn_kopen.c:811-854: Simpson's rule with 2 x 20 intervals over x in [b, x0] of
+//        f(x) = 2 tan(th) (x - b) sqrt(r^2 - x^2 - tan^2(th) (x - b)^2).
+// At the sample points x = b + i h the radicand is a quadratic in i,
+//        a3(i) = (r^2 - b^2) - 2 b h i - (1 + tan^2) h^2 i^2,
+// evaluated by Horner's rule (2 FMAs instead of the reference's 6 unfused operations; the absolute error stays
+// ~1e-16 r^2 as in the reference's own form, and the |a3| < 1e-10 clamp of :867 is applied to it the same way), and
+// f = (2 tan h i) sqrt(a3).  The reference's (double)(float) loop factors are small integers, exact in either type.
 __device__ __noinline__ double triang(double b, double r, const Ang& a)
 {
     double sint = a.s, cost = a.c;
@@ -111,13 +132,24 @@ __device__ __noinline__ double triang(double b, double r, const Ang& a)
     double x0 = b * (sint * sint) + sqrt(a1) * cost;
     const int m = LUT_NOINT;
     double h = .50 * (x0 - b) / (double) (float) m;
-    double sum1 = 0.0;
-#pragma unroll 4
-    for (int i = 0; i < m; i++) sum1 += triang_fcn(b + (double) (float) (2 * i + 1) * h, b, r, a.t);
+    const double c0 = r * r - b * b, c1 = -2.0 * b * h, c2 = -(1.0 + a.t * a.t) * (h * h), d = 2.0 * a.t * h;
+    double sum1 = 0.0, sum2 = 0.0, f = 1.0;
+#pragma unroll 2
+    for (int i = 0; i < m - 1; i++, f += 2.0) {
+        double q1 = fma(fma(c2, f, c1), f, c0);
+        if (fabs(q1) < 0.0000000001) q1 = 0.0;
+        sum1 += (d * f) * sqrt_lite(q1);                         // odd points 1, 3, .., 37
+        const double g = f + 1.0;
+        double q2 = fma(fma(c2, g, c1), g, c0);
+        if (fabs(q2) < 0.0000000001) q2 = 0.0;
+        sum2 += (d * g) * sqrt_lite(q2);                         // even points 2, 4, .., 38
+    }
+    {
+        double q1 = fma(fma(c2, f, c1), f, c0);                  // point 39
+        if (fabs(q1) < 0.0000000001) q1 = 0.0;
+        sum1 += (d * f) * sqrt_lite(q1);
+    }
     double volume = 4.0 * sum1;
-    double sum2 = 0.0;
-#pragma unroll 4
-    for (int i = 0; i < m - 1; i++) sum2 += triang_fcn(b + (double) (float) (2 * (i + 1)) * h, b, r, a.t);
     volume += 2.0 * sum2;
     volume += triang_fcn(x0, b, r, a.t);
     volume += triang_fcn(b, b, r, a.t);
@@ -248,32 +280,42 @@ __device__ double expected_single_crown_path(const Crown& c, const Ang& a, doubl
     return ES;
 }
 
-// lut_full_kernel: one CTA per GROUP of consecutive parameter sets that share (r, b, h1, h2) bit for bit (capped at
-// group_cap <= LUT_GROUP_CAP sets, chunk boundaries at multiples of the cap).
+// ------------------------------------------------------------------------------------------------------------------
+// The full gap-probability path as a PIPELINE OF FLAT KERNELS (round 2).
 //
-// Work decomposition (round 2).  The reference's nest is  zenith t (91) x entry height sp_i (13) x crown count n (30)
-// (gortt_pn_kopen.c:457-527).  Round 1 gave every zenith ONE thread that walked the 13 entry heights serially and kept
-// v_g[15], s'[13] and the 13 tube-volume differences in registers (96 registers, 3 warps per CTA, 22.7 % of the SM's
-// warp slots, FP64 pipe 45 % busy, 98 % of the EnKF member update).  Now a CTA is 96 x LUT_NK threads: lane = zenith
-// (neighbouring zeniths take the same branches of the sphere / cylinder geometry), and the entry heights -- and the
-// 14 + K distinct cross-sections of phase 1 -- are dealt round-robin to the LUT_NK thread rows; the per-zenith arrays
-// live in shared memory, so a thread carries one entry height at a time (<= 80 registers, two 384-thread CTAs per SM).
-//   phase 1, once per group: everything that depends on crown shape and zenith only -- the projected cross-section
-//            volumes v_g[h][t] (gortt_pn_kopen.c:24-32, :149-323), E[S] (:534-563), and for every entry height the
-//            tube-volume difference of :496 (Simpson rule, sphere/cylinder sections);
-//   phase 2, per sub-group of up to SUB members that also share the stem density: p_n0 = exp(-lv' v_g), then the
-//            crown-count loop (:489-527) once per entry height; per member only the within-crown gap sums.
-// The bin attenuation exp(-s_bin tau') of gortt_calc_epgap (:1110-1114) depends on (set, bin) only -- not on zenith,
-// entry height or crown count -- so it is TABULATED once per member (LUT_TAB bins, one exp each, the literal formula)
-// instead of being re-evaluated at every change of bin inside the crown-count loop (~10 exp per (zenith, entry height)
-// before: the largest single item of a set with its own crown shape).
-// Each thread row accumulates its entry heights in the reference's order and the LUT_NK partial sums are added in a fixed
-// order: the same terms as the reference's bin-by-bin sum in a different association (~1e-16 relative).
+// The reference's nest is  zenith t (91) x entry height sp_i (13) x crown count n (30)  (gortt_pn_kopen.c:457-527)
+// behind a shape-only geometry phase (cross-sections :149-323, tube volumes :665-924).  Round 1 ran all of it in one
+// kernel, one thread per zenith: 96 registers, 3 warps per CTA, 22.7 % of the warp slots, FP64 pipe 45 % busy, 78 KB of
+// code executed by warps in different phases (instruction-fetch stalls), 98 % of the EnKF member update.  A first
+// restructuring inside one kernel (entry heights dealt to four thread rows) stayed barrier- and fetch-bound (ncu:
+// 2.6 barrier-stalled and 1.0 fetch-stalled warps per issue).  Now every phase is its own small kernel in which a WARP
+// is one (item, 32 consecutive zeniths) pair -- neighbouring zeniths take the same branches of the sphere / cylinder
+// geometry -- every warp of a CTA does the same amount of work, and the per-zenith arrays travel through HBM / L2
+// (24.5 KB per crown shape, ~1 ms per 10^5 shapes, against ~20 ms of arithmetic):
+//
+//   lut_plan_kernel     per set: head of its shape group (consecutive sets sharing r, b, h1, h2 bit for bit, capped),
+//                       head and size of its sub-group (group members that also share the stem density, <= LUT_SUB)
+//   lut_prep_kernel     per (shape, zenith): theta', its sin / cos / tan, E[S]                   gortt.c:783-797, :534-563
+//   lut_vg_kernel       per (shape, zenith third): warp = cross-section j, then warp = layer h   gortt_pn_kopen.c:24-32, :149-323
+//   lut_tube_kernel     per (shape, zenith third): warp = entry height: tube-volume difference   :496, :665-924
+//   lut_crown_kernel    per (sub-group, zenith third): warp = entry height: the crown-count loop :489-527, once per
+//                       sub-group; per member only the within-crown gap sums; 13 partial sums added in a fixed order
+//   kopen_kernel        per set: trapezoid rule over the 91 zeniths                              :351-375
+//
+// Shape groups and sub-groups keep what round 1 introduced: LUT grids and ensembles that vary stem density / leaf
+// area over fixed crown shapes (BASELINE.json configs 4a and 5) pay the geometry once per group and the crown-count
+// loop once per sub-group.  The bin attenuation exp(-s_bin tau') of gortt_calc_epgap (:1110-1114) depends on (set, bin)
+// only -- not on zenith, entry height or crown count -- so it is tabulated once per member and zenith third (LUT_TAB
+// bins, one exp each, the literal formula) instead of being evaluated at every change of bin inside the crown-count
+// loop (~10 exp per (zenith, entry height) before).
+// A set gets the same bits alone, inside a group or sub-group, or at a chunk boundary.
 #define LUT_GROUP_CAP 64
-#define LUT_NK 4                        // thread rows per CTA (entry heights / cross-sections dealt round-robin)
-#define LUT_CTA (LUT_THREADS * LUT_NK)
+#define LUT_SUB 8                       // members per sub-group (same shape AND same stem density)
+#define LUT_NSP (GORT_NLAYERS - 2)     // entry heights sp_i = 1 .. 13 (sp_i = 14 contributes p_s0 = 0)
+#define LUT_ZW 96                       // zenith slots per set in the workspace arrays (3 warps)
 #define LUT_TAB 512                     // tabulated bins of exp(-s_bin tau'); bins beyond use the formula directly
 #define LUT_NA 32                       // distinct cross-sections per zenith: 14 + K, K < 16
+#define LUT_CHUNK 16384                 // sets per pass: bounds the workspace (24.5 KB per set)
 // 1/n!, n = 0..30, each the FP64 quotient 1.0 / n! (the reference tabulates n! in gortt.c:752-754 and divides)
 __constant__ double c_inv_fact[LUT_MAXCROWNS + 1] = {
     1.0,
@@ -307,8 +349,16 @@ __constant__ double c_inv_fact[LUT_MAXCROWNS + 1] = {
     3.2798892370698385e-30,
     1.1309962886447718e-31,
     3.769987628815906e-33};
-#define LUT_SUB 8                       // members per sub-group (same shape AND same stem density)
-#define LUT_NSP (GORT_NLAYERS - 2)     // entry heights sp_i = 1 .. 13 (sp_i = 14 contributes p_s0 = 0)
+
+// Workspace of one pass (n = sets of the pass), all per set index of the pass; shape-level rows are filled for group
+// heads only.
+struct LutWork {
+    int *head;          // [n]      index of the set's group head
+    int *sub;           // [n]      sub-group size if the set is a sub-group head, else 0
+    double *trig;       // [n][4][LUT_ZW]    sin, cos, tan of theta', E[S]
+    double *vg;         // [n][15][LUT_ZW]   v_g[h][t]
+    double *tube;       // [n][13][LUT_ZW]   tube-volume difference per entry height
+};
 
 __device__ __forceinline__ bool same_shape(const double* __restrict__ st, size_t n, int a, int b)
 {
@@ -316,217 +366,258 @@ __device__ __forceinline__ bool same_shape(const double* __restrict__ st, size_t
            st[3 * n + a] == st[3 * n + b] && st[4 * n + a] == st[4 * n + b];
 }
 
+// Crown shape of set m: gortt_init_params, gortt.c:641-697 (the shape-only part)
+struct Shape { Crown c; double ellip, h1, h2, z2, dz; };
+__device__ __forceinline__ Shape shape_load(const double* __restrict__ structure, size_t N, int m)
+{
+    Shape S;
+    const double r = structure[1 * N + m], b = structure[2 * N + m];
+    S.h1 = structure[3 * N + m]; S.h2 = structure[4 * N + m];
+    S.ellip = b / r;
+    S.c.r = r; S.c.rr = r * r; S.c.rrr = S.c.rr * r;
+    const double z1 = S.h1 - r * S.ellip;
+    S.z2 = S.h2 + r * S.ellip;
+    S.c.z2_p = S.z2 / S.ellip;
+    S.c.h1_p = S.h1 / S.ellip;
+    S.c.h2_p = S.h2 / S.ellip;
+    S.dz = (double) (S.z2 - z1) / ((double) GORT_NLAYERS - 1.0);
+    S.c.ds = S.dz;
+    S.c.dz_p = S.dz / S.ellip;
+    S.c.lv_p = 0.0; S.c.tau_p = 0.0;
+    return S;
+}
+// height_p[i], gortt.c:778-781
+__device__ __forceinline__ double layer_height_p(const Shape& S, int i)
+{
+    return (S.z2 - S.dz * (double) (GORT_NLAYERS - 1 - i)) / S.ellip;
+}
+
+// Groups and sub-groups.  m0 + i is the global index of set i of this pass: group boundaries sit at multiples of
+// group_cap of the GLOBAL index (and at the start of a pass), so the partition does not depend on the pass size.
+__global__ void __launch_bounds__(128)
+lut_plan_kernel(int n, int m0, int group_cap, const double* __restrict__ structure, size_t N, LutWork w)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int m = m0 + i;
+    // group head: walk back while the predecessor has the same shape and no boundary is crossed
+    int h = i;
+    while (h > 0 && ((m0 + h) % group_cap) != 0 && same_shape(structure, N, m0 + h, m0 + h - 1)) h--;
+    w.head[i] = h;
+    // sub-groups: the run of equal stem density that contains m, inside the group, cut every LUT_SUB members
+    const double lambda = structure[0 * N + m];
+    int rs = i;
+    while (rs > h && structure[0 * N + m0 + rs - 1] == lambda) rs--;
+    int nj = 0;
+    if ((i - rs) % LUT_SUB == 0) {
+        nj = 1;
+        while (nj < LUT_SUB && i + nj < n && ((m0 + i + nj) % group_cap) != 0 &&
+               same_shape(structure, N, m0 + i + nj, m0 + i + nj - 1) && structure[0 * N + m0 + i + nj] == lambda) nj++;
+    }
+    w.sub[i] = nj;
+}
+
+// theta' and its trig, E[S]: one thread per (group head, zenith)
+__global__ void __launch_bounds__(128)
+lut_prep_kernel(int n, int m0, const double* __restrict__ structure, size_t N, LutWork w)
+{
+    const long e = (long) blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = (int) (e / LUT_ZW), t = (int) (e - (long) i * LUT_ZW);
+    if (i >= n || w.head[i] != i || t >= GORT_NTH) return;
+    const Shape S = shape_load(structure, N, m0 + i);
+    const double dth = 1 * GORT_PI / 180.0;
+    double theta = dth * (double) t;                                             // gortt.c:783-797
+    if (theta >= GORT_PI / 2.0) theta = GORT_PI / 2.0 - 1.0 * GORT_PI / 180.0;
+    double th = atan(tan(theta) * S.ellip);
+    if (th >= GORT_PI / 2.0) th = GORT_PI / 2.0 - 1.0 * GORT_PI / 180.0;
+    Ang a;
+    a.th = th; a.s = sin(th); a.c = cos(th); a.t = tan(th);
+    double* o = w.trig + (size_t) i * 4 * LUT_ZW + t;
+    o[0 * LUT_ZW] = a.s; o[1 * LUT_ZW] = a.c; o[2 * LUT_ZW] = a.t;
+    o[3 * LUT_ZW] = t < GORT_NTH - 1 ? expected_single_crown_path(S.c, a, layer_height_p(S, 0)) : 0.0;   // :445
+}
+
+__device__ __forceinline__ Ang ang_load(const LutWork& w, int i, int t)
+{
+    const double* o = w.trig + (size_t) i * 4 * LUT_ZW + t;
+    Ang a;
+    a.th = 0.0; a.s = o[0 * LUT_ZW]; a.c = o[1 * LUT_ZW]; a.t = o[2 * LUT_ZW];
+    return a;
+}
+
+// v_g[h][t], gortt_pn_kopen.c:29, :149-167: midpoint rule over the crown-centre height z of the projected cross-section
+// of a crown centred at z seen from layer height h.  The cross-section depends on h - z only, the layer heights and
+// the midpoints are both dz' apart, so the 15 x K evaluations take only 14 + K distinct values: each is evaluated once
+// (at its first (h, z) pair) and the 15 sums are formed in the reference's order.  (The other pairs differ from it by
+// the rounding of h - z, ~1e-16.)  One thread per (group head, zenith); its cross-sections sit in its own column of
+// shared memory (no barrier: nobody else reads them).
+#define LUT_VG_THREADS 128
+__global__ void __launch_bounds__(LUT_VG_THREADS, 6)
+lut_vg_kernel(int n, int m0, const double* __restrict__ structure, size_t N, LutWork w)
+{
+    __shared__ double s_A[LUT_NA][LUT_VG_THREADS];
+    const long e = (long) blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = (int) (e / LUT_ZW), t = (int) (e - (long) i * LUT_ZW);
+    if (i >= n || w.head[i] != i || t >= GORT_NTH) return;
+    const Shape S = shape_load(structure, N, m0 + i);
+    const Ang a = ang_load(w, i, t);
+    double* vg = w.vg + (size_t) i * GORT_NLAYERS * LUT_ZW + t;
+    // crown-centre heights of the midpoint rule, gortt_pn_kopen.c:162: a running sum
+    double zk[16];
+    int K = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) zk[k] = 0.0;
+    {
+        double z = S.c.h1_p + S.c.dz_p / 2.0;
+#pragma unroll
+        for (int k = 0; k < 16; k++) { if (z <= S.c.h2_p && K == k) { zk[k] = z; K = k + 1; z += S.c.dz_p; } }
+        if (K == 16 && z <= S.c.h2_p) K = 17;                    // more than 16 midpoints: the literal rule below
+    }
+    if (K < 1 || K >= 16) {
+#pragma unroll 1
+        for (int h = 0; h < GORT_NLAYERS; h++) vg[(size_t) h * LUT_ZW] = proj_volume(S.c, a, layer_height_p(S, h));
+        return;
+    }
+    // distinct cross-sections j = 0 .. 13 + K: (h, z) = (0, K-1-j) for j < K, (j-K+1, 0) after
+    double zsel = 0.0;
+#pragma unroll 1
+    for (int j = 0; j < GORT_NLAYERS + K - 1; j++) {
+        const int ih = max(0, j - (K - 1)), k = ih - (j - (K - 1));
+#pragma unroll
+        for (int q = 0; q < 16; q++) if (q == k) zsel = zk[q];
+        s_A[j][threadIdx.x] = cross_section(S.c, a, layer_height_p(S, ih), zsel);
+    }
+#pragma unroll 1
+    for (int h = 0; h < GORT_NLAYERS; h++) {
+        double vol = 0.0;
+        for (int k = 0; k < K; k++) vol += s_A[h - k + K - 1][threadIdx.x] * (S.c.dz_p);
+        vg[(size_t) h * LUT_ZW] = vol;
+    }
+}
+
+// Tube-volume difference per entry height, gortt_pn_kopen.c:496.  CTA = (group head, zenith third), warp = entry height.
+__global__ void __launch_bounds__(32 * LUT_NSP, 3)
+lut_tube_kernel(int n, int m0, const double* __restrict__ structure, size_t N, LutWork w)
+{
+    const int i = blockIdx.x;
+    if (w.head[i] != i) return;
+    const int lane = threadIdx.x & 31, k = threadIdx.x >> 5;
+    const int t = blockIdx.y * 32 + lane;
+    if (t >= GORT_NTH - 1) return;                                               // epgap only for t < nth - 1, :1099
+    const Shape S = shape_load(structure, N, m0 + i);
+    const Ang a = ang_load(w, i, t);
+    const double hp0 = layer_height_p(S, 0);
+    const double hps = layer_height_p(S, GORT_NLAYERS - 2 - k);                  // :457, sp_i = 13 down to 1
+    w.tube[((size_t) i * LUT_NSP + k) * LUT_ZW + t] = tube_vol(S.c, a, hp0, hps, S.c.h2_p) - tube_vol(S.c, a, hp0, hps, S.c.h1_p);
+}
+
+// Crown-count loop and within-crown gap sums.  CTA = (sub-group head, zenith third), warp = entry height.
 template <int SUB>
-struct LutSmem {
-    double hp[GORT_NLAYERS];                 // height_p
-    double zk[16];                           // crown-centre heights of the midpoint rule
-    int K;
-    double ang[4][LUT_THREADS];              // theta_p, sin, cos, tan per zenith
-    double es[LUT_THREADS];                  // E[S] per zenith
-    union {                                  // A is dead once v_g is summed (a barrier before the first use of part)
-        double A[LUT_NA][LUT_THREADS];           // distinct cross-sections
-        double part[LUT_NK][SUB][LUT_THREADS];   // partial within-crown gap sums per thread row
-    };
-    double vg[GORT_NLAYERS][LUT_THREADS];    // v_g[h][t]
-    double pn0[GORT_NLAYERS][LUT_THREADS];   // p_n0[h][t] of the current sub-group
-    double tube[LUT_NSP][LUT_THREADS];       // tube-volume difference per entry height
-    double tab[SUB][LUT_TAB];                // exp(-s_bin tau') per member of the current sub-group
+struct CrownSmem {
+    double tab[SUB][LUT_TAB];                // exp(-s_bin tau') per member
+    double part[LUT_NSP][SUB][32];           // partial within-crown gap sums per entry height
 };
 
 template <int SUB>
-__global__ void __launch_bounds__(LUT_CTA, 2)
-lut_full_kernel(int n_sets, int group_cap, const double* __restrict__ structure, double* __restrict__ lut)
+__global__ void __launch_bounds__(32 * LUT_NSP, SUB == 1 ? 3 : 2)
+lut_crown_kernel(int n, int m0, const double* __restrict__ structure, size_t N, LutWork w, double* __restrict__ lut)
 {
-    extern __shared__ __align__(16) unsigned char lut_smem_raw[];
-    LutSmem<SUB>& sm = *reinterpret_cast<LutSmem<SUB>*>(lut_smem_raw);
-    const int m0 = blockIdx.x;
-    const int tid = threadIdx.x;
-    const int t = tid % LUT_THREADS;             // zenith index (lanes of a warp: consecutive zeniths)
-    const int kk = tid / LUT_THREADS;            // thread row
-    const size_t N = (size_t) n_sets;
-    // group heads: a set whose crown shape differs from its predecessor's, or that sits on a chunk boundary
-    if (m0 > 0 && (m0 % group_cap) != 0 && same_shape(structure, N, m0, m0 - 1)) return;
-    int m1 = m0 + 1;
-    while (m1 < n_sets && (m1 % group_cap) != 0 && same_shape(structure, N, m1, m1 - 1)) m1++;
-    // two instantiations share the work: SUB = 1 takes the groups whose members all differ in stem density -- in
-    // particular every single-set group --, SUB = LUT_SUB takes the groups that start with a sub-group (same stem
-    // density, favd varying)
-    {
-        const bool shares = (m1 - m0 >= 2) && structure[0 * N + m0] == structure[0 * N + m0 + 1];
-        if ((SUB == 1) == shares) return;
+    extern __shared__ __align__(16) unsigned char crown_smem_raw[];
+    CrownSmem<SUB>& sm = *reinterpret_cast<CrownSmem<SUB>*>(crown_smem_raw);
+    double (*s_tab)[LUT_TAB] = sm.tab;
+    double (*s_part)[SUB][32] = sm.part;
+    const int i = blockIdx.x;
+    const int nj = w.sub[i];
+    // two instantiations share the sub-groups: SUB = 1 takes the single-member ones, SUB = LUT_SUB the others
+    if (nj == 0 || (SUB == 1) != (nj == 1)) return;
+    const int hd = w.head[i];
+    const int lane = threadIdx.x & 31, k = threadIdx.x >> 5;
+    const int t = blockIdx.y * 32 + lane;
+    const int m = m0 + i;
+    const Shape S = shape_load(structure, N, m);
+    const double lambda = structure[0 * N + m];
+    const double lv = lambda / (S.h2 - S.h1);
+    const double lv_p = lv * S.ellip;
+    // bin attenuations of the sub-group's members: exp(-s_bin tau'), s_bin = bin * ds, tau' = k favd'  (:1110-1114).
+    // Bins in use: s < n E[S] <= 30 * (21/20) * 4r/3 = 42 r  (s = s'(1 - e^(-n E[S]/s')) < n E[S]; E[S] is a 20- or
+    // 21-term midpoint sum of 4r/3 (:534-563)), so only bins up to 42 r / ds + 1 are ever addressed.
+    const int n_tab = (int) fmin((double) LUT_TAB, 42.0 * S.c.r / S.c.ds + 2.0);
+    for (int e = threadIdx.x; e < nj * n_tab; e += 32 * LUT_NSP) {
+        const int j = e / n_tab, bin = e - j * n_tab;
+        const double favd_p = structure[5 * N + m + j] * S.ellip;
+        const double sbin = (double) bin * S.c.ds;
+        s_tab[j][bin] = exp(-sbin * (0.5 * favd_p));
     }
-
-    // ---- gortt_init_params, gortt.c:641-697: the shape-only part ------------------------------------
-    const double r      = structure[1 * N + m0];
-    const double b      = structure[2 * N + m0];
-    const double h1     = structure[3 * N + m0];
-    const double h2     = structure[4 * N + m0];
-    const double ellip = b / r;
-    Crown c;
-    c.r = r; c.rr = r * r; c.rrr = c.rr * r;
-    const double z1 = h1 - r * ellip;
-    const double z2 = h2 + r * ellip;
-    c.z2_p = z2 / ellip;
-    c.h1_p = h1 / ellip;
-    c.h2_p = h2 / ellip;
-    const double dz = (double) (z2 - z1) / ((double) GORT_NLAYERS - 1.0);
-    c.ds = dz;
-    c.dz_p = dz / ellip;
-    c.lv_p = 0.0; c.tau_p = 0.0;                 // per member, below
-    if (tid < GORT_NLAYERS) {                                                    // gortt.c:778-781
-        double height = z2 - dz * (double) (GORT_NLAYERS - 1 - tid);
-        sm.hp[tid] = height / ellip;
-    }
-    if (tid == LUT_THREADS) {
-        // crown-centre heights of the midpoint rule, gortt_pn_kopen.c:162: a running sum
-        int K = 0;
-        for (double z = c.h1_p + c.dz_p / 2.0; z <= c.h2_p && K < 16; z += c.dz_p) sm.zk[K++] = z;
-        sm.K = K;
-    }
-    const double dth = 1 * GORT_PI / 180.0;
-    if (kk == LUT_NK - 1 && t < GORT_NTH) {
-        double theta = dth * (double) t;                                         // gortt.c:783-797
-        if (theta >= GORT_PI / 2.0) theta = GORT_PI / 2.0 - 1.0 * GORT_PI / 180.0;
-        double th = atan(tan(theta) * ellip);
-        if (th >= GORT_PI / 2.0) th = GORT_PI / 2.0 - 1.0 * GORT_PI / 180.0;
-        sm.ang[0][t] = th; sm.ang[1][t] = sin(th); sm.ang[2][t] = cos(th); sm.ang[3][t] = tan(th);
-    }
+    const bool live = t < GORT_NTH, path = t < GORT_NTH - 1;
+    double e_t[SUB];
+#pragma unroll
+    for (int j = 0; j < SUB; j++) e_t[j] = 0.0;
+    const double* vg = w.vg + (size_t) hd * GORT_NLAYERS * LUT_ZW + t;
+    double pn0_0 = 0.0;
+    if (live && k == 0) pn0_0 = exp(-1.0 * lv_p * vg[0]);                        // gortt_pn_kopen.c:30: the p_n0 row of the LUT
     __syncthreads();
-    Ang a;
-    a.th = a.s = a.c = a.t = 0.0;
-    const bool live = t < GORT_NTH;               // 91 of 96 lanes
-    const bool path = t < GORT_NTH - 1;           // epgap only for t < nth - 1, gortt_pn_kopen.c:1099
-    if (live) { a.th = sm.ang[0][t]; a.s = sm.ang[1][t]; a.c = sm.ang[2][t]; a.t = sm.ang[3][t]; }
-    const int K = sm.K;
-    const bool tabulated = K >= 1 && K < 16;
-    const double hp0 = sm.hp[0];
-
-    // ---- phase 1 -----------------------------------------------------------------------------------
-    if (live) {
-        // v_g[h][t], gortt_pn_kopen.c:29, :149-167: midpoint rule over the crown-centre height z of the projected
-        // cross-section of a crown centred at z seen from layer height h.  The cross-section depends on h - z only,
-        // the layer heights and the midpoints are both dz' apart, so the 15 x K evaluations take only 14 + K distinct
-        // values: each is evaluated once (at its first (h, z) pair) and the 15 sums are formed in the reference's
-        // order.  (The other pairs differ from it by the rounding of h - z, ~1e-16.)
-        if (tabulated) {
+    if (path) {
+        const double* tr = w.trig + (size_t) hd * 4 * LUT_ZW + t;
+        const double a_c = tr[1 * LUT_ZW], es = tr[3 * LUT_ZW];
+        const int sp_i = GORT_NLAYERS - 2 - k;
+        const double P_s_p = exp(-1.0 * lv_p * vg[(size_t) (sp_i + 1) * LUT_ZW]) - exp(-1.0 * lv_p * vg[(size_t) sp_i * LUT_ZW]);   // :43, :482
+        const double temp1 = w.tube[((size_t) hd * LUT_NSP + k) * LUT_ZW + t] * lv_p;   // :497
+        const double E = exp(-temp1);
+        const double hp0 = layer_height_p(S, 0);
+        const double sp = (double) (layer_height_p(S, sp_i) - hp0) / a_c;       // :464
+        // crown-count loop, gortt_pn_kopen.c:489-527, with its loop invariants hoisted:
+        //   P(n) P(s') = temp1^n e^-temp1 / (n! (1 - e^-temp1)) P(s')        :501-502, :522
+        //   s          = s' (1 - exp(-n E[S]/s'))                            :508
+        // exp(-n x) is advanced as q^n (q = exp(-x)) and s/ds + 0.5 formed with one FMA; because s selects a histogram
+        // bin through (int)(s/ds + 0.5) (:134-139, :522) the literal formula is evaluated instead whenever the fast
+        // form lands within 1e-9 of a bin boundary, so the bin is always the one the literal formula gives.
+        const double c0 = E / (1.0 - E) * P_s_p;
+        const double q = exp(-(es / sp));
+        const double spd = sp * (1.0 / S.c.ds), spd5 = spd + 0.5;
+        double pw = c0, qn = 1.0;
 #pragma unroll 1
-            for (int j = kk; j < GORT_NLAYERS + K - 1; j += LUT_NK) {
-                const int i = max(0, j - (K - 1)), k = i - (j - (K - 1));
-                sm.A[j][t] = cross_section(c, a, sm.hp[i], sm.zk[k]);
+        for (int nn = 1; nn <= LUT_MAXCROWNS; nn++) {                            // :489
+            pw *= temp1;                                                         // temp1^n e^-t / (1 - e^-t) P(s')
+            qn *= q;
+            const double wgt = pw * c_inv_fact[nn];
+            double u = fma(-spd, qn, spd5);
+            // nearest integer and floor of u (0 <= u < 2^31) without the conversion unit: adding 1.5 * 2^52 leaves
+            // round-to-nearest(u) in the low word of the sum
+            double v = u + 6755399441055744.0;
+            double dlt = u - (v - 6755399441055744.0);
+            if (fabs(dlt) < 1e-9) {
+                u = sp * (1.0 - exp(-1.0 * (double) nn * es / sp)) / S.c.ds + 0.5;       // the literal formula, :508, :134-139
+                v = u + 6755399441055744.0;
+                dlt = u - (v - 6755399441055744.0);
             }
-        } else {
-#pragma unroll 1
-            for (int h = kk; h < GORT_NLAYERS; h += LUT_NK) sm.vg[h][t] = proj_volume(c, a, sm.hp[h]);
-        }
-        if (path) {
-            if (kk == 0) sm.es[t] = expected_single_crown_path(c, a, hp0);      // :445
-#pragma unroll 1
-            for (int k = kk; k < LUT_NSP; k += LUT_NK) {
-                const double hps = sm.hp[GORT_NLAYERS - 2 - k];                  // :457, sp_i = 13 down to 1
-                sm.tube[k][t] = tube_vol(c, a, hp0, hps, c.h2_p) - tube_vol(c, a, hp0, hps, c.h1_p);   // :496
-            }
-        }
-    }
-    __syncthreads();
-    if (live && tabulated) {
-#pragma unroll 1
-        for (int h = kk; h < GORT_NLAYERS; h += LUT_NK) {
-            double vol = 0.0;
-            for (int k = 0; k < K; k++) vol += sm.A[h - k + K - 1][t] * (c.dz_p);
-            sm.vg[h][t] = vol;
-        }
-    }
-    // (the barrier that publishes vg is the first one of the member loop)
-
-    // ---- members of the group, in sub-groups of up to SUB consecutive members that also share the stem
-    //      density: p_n0, P(n) and the bin sequence depend on lambda only, favd enters through the bin attenuation
-    //      exp(-s_bin tau') alone (gortt_pn_kopen.c:1110-1114), so the crown-count loop runs once per sub-group
-    //      and only the sums are per member ----
-    const double inv_ds = 1.0 / c.ds;
-    for (int ms = m0; ms < m1;) {
-        const double lambda = structure[0 * N + ms];
-        int nj = 1;
-        while (nj < SUB && ms + nj < m1 && structure[0 * N + ms + nj] == lambda) nj++;
-        const double lv = lambda / (h2 - h1);
-        const double lv_p = lv * ellip;
-        __syncthreads();                                 // vg complete; previous sub-group done with pn0 / tab / part
-        // bin attenuations of the sub-group's members: exp(-s_bin tau'), s_bin = bin * ds, tau' = k favd'  (:1110-1114)
-        for (int i = tid; i < nj * LUT_TAB; i += LUT_CTA) {
-            const int j = i / LUT_TAB, bin = i - j * LUT_TAB;
-            const double favd_p = structure[5 * N + ms + j] * ellip;
-            const double sbin = (double) bin * c.ds;
-            sm.tab[j][bin] = exp(-sbin * (0.5 * favd_p));
-        }
-        if (live) {
-#pragma unroll 1
-            for (int h = kk; h < GORT_NLAYERS; h += LUT_NK) sm.pn0[h][t] = exp(-1.0 * lv_p * sm.vg[h][t]);   // gortt_pn_kopen.c:30
-        }
-        __syncthreads();
-        double e_t[SUB], tau[SUB];
+            const int idx = __double2loint(v) - (dlt < 0.0 ? 1 : 0);                       // (int) u
+            // gortt_calc_epgap + gortt_calc_pgap, :1110-1114, :1138
+            if (idx >= 0 && idx < n_tab) {
 #pragma unroll
-        for (int j = 0; j < SUB; j++) {
-            e_t[j] = 0.0;
-            tau[j] = 0.5 * (structure[5 * N + ms + (j < nj ? j : 0)] * ellip);
-        }
-        if (path) {
-            const double es = sm.es[t];
-#pragma unroll 1
-            for (int k = kk; k < LUT_NSP; k += LUT_NK) {
-                const int sp_i = GORT_NLAYERS - 2 - k;
-                const double P_s_p = sm.pn0[sp_i + 1][t] - sm.pn0[sp_i][t];      // :43, :482
-                const double temp1 = sm.tube[k][t] * lv_p;                       // :497
-                const double E = exp(-temp1);
-                const double sp = (double) (sm.hp[sp_i] - hp0) / a.c;            // :464
-                // crown-count loop, gortt_pn_kopen.c:489-527, with its loop invariants hoisted:
-                //   P(n) = temp1^n e^-temp1 / (n! (1 - e^-temp1))             :501-502
-                //   s    = s' (1 - exp(-n E[S]/s'))                            :508
-                // exp(-n x) is advanced as q^n (q = exp(-x)); because s selects a histogram bin through
-                // (int)(s/ds + 0.5) (:134-139, :522) the literal exp is evaluated instead whenever the
-                // product form (with s/ds as s * (1/ds)) lands within 1e-9 of a bin boundary, so the bin is
-                // always the one the literal formula gives.
-                const double c0 = E / (1.0 - E);
-                const double x = es / sp;
-                const double q = exp(-x);
-                double pw = 1.0, qn = 1.0;
-#pragma unroll 1
-                for (int n = 1; n <= LUT_MAXCROWNS; n++) {                       // :489
-                    pw *= temp1;                                                 // temp1^n
-                    qn *= q;
-                    const double P_n = pw * c0 * c_inv_fact[n];
-                    double u = sp * (1.0 - qn) * inv_ds + 0.5;
-                    if (fabs(u - rint(u)) < 1e-9)
-                        u = sp * (1.0 - exp(-1.0 * (double) n * es / sp)) / c.ds + 0.5;
-                    const int idx = (int) u;
-                    const double wgt = P_n * P_s_p;
-                    // gortt_calc_epgap + gortt_calc_pgap, :1110-1114, :1138
-                    if (idx >= 0 && idx < LUT_TAB) {
+                for (int j = 0; j < SUB; j++) e_t[j] = fma(s_tab[j][idx], wgt, e_t[j]);
+            } else {
+                const double sbin = (double) idx * S.c.ds;
 #pragma unroll
-                        for (int j = 0; j < SUB; j++) e_t[j] += sm.tab[j][idx] * wgt;
-                    } else {
-                        const double sbin = (double) idx * c.ds;
-#pragma unroll
-                        for (int j = 0; j < SUB; j++) e_t[j] += exp(-sbin * tau[j]) * wgt;
-                    }
+                for (int j = 0; j < SUB; j++) {                                  // beyond the table: the formula itself
+                    const double tau_j = 0.5 * (structure[5 * N + m + (j < nj ? j : 0)] * S.ellip);
+                    e_t[j] = fma(exp(-sbin * tau_j), wgt, e_t[j]);
                 }
             }
         }
-        if (live) {
+    }
 #pragma unroll
-            for (int j = 0; j < SUB; j++) sm.part[kk][j][t] = e_t[j];
-        }
-        __syncthreads();
-        // the openness factors (trapezoid rule over the 91 zeniths) are formed by kopen_kernel afterwards
-        if (live) {
-            for (int j = kk; j < nj; j += LUT_NK) {
-                double e = sm.part[0][j][t];
+    for (int j = 0; j < SUB; j++) s_part[k][j][lane] = e_t[j];
+    __syncthreads();
+    // rows of the LUT record: p_n0[0][t] and epgap[0][t] (the 13 entry heights added in the reference's order, :457);
+    // the openness factors are formed by kopen_kernel afterwards
+    if (live) {
+        if (k == 0) for (int j = 0; j < nj; j++) lut[(size_t) (m + j) * GORT_LUT_STRIDE + t] = pn0_0;
+        for (int j = k; j < nj; j += LUT_NSP) {
+            double e = s_part[0][j][lane];
 #pragma unroll
-                for (int q2 = 1; q2 < LUT_NK; q2++) e += sm.part[q2][j][t];
-                double* o = lut + (size_t) (ms + j) * GORT_LUT_STRIDE;
-                o[t] = sm.pn0[0][t];
-                o[GORT_NTH + t] = e;
-            }
+            for (int q2 = 1; q2 < LUT_NSP; q2++) e += s_part[q2][j][lane];
+            lut[(size_t) (m + j) * GORT_LUT_STRIDE + GORT_NTH + t] = e;
         }
-        ms += nj;
     }
 }
 
@@ -613,25 +704,44 @@ kopen_kernel(int n_sets, double* __restrict__ lut)
 int launch_lut(gort_ctx *ctx, cudaStream_t s, int n_sets, const double *structure, int method, double *lut)
 {
     note_other_work(ctx);
-    if (method == GORT_LUT_Q08) lut_q08_kernel<<<n_sets, LUT_THREADS, 0, s>>>(n_sets, structure, lut);
-    else {
-        // group cap: as large as possible (phase 1 is shared by the whole group) while the batch still yields
-        // enough groups to fill the GPU a few times over; results do not depend on it
-        int cap = n_sets / (ctx->sm_count * 12);
-        if (cap < 1) cap = 1;
-        if (cap > LUT_GROUP_CAP) cap = LUT_GROUP_CAP;
-        static_assert(sizeof(LutSmem<LUT_SUB>) <= 113 * 1024, "two LUT CTAs per SM");
-        if (!ctx->lut_attr_set) {
-            cudaError_t e = cudaFuncSetAttribute(lut_full_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LutSmem<1>));
-            if (e == cudaSuccess) e = cudaFuncSetAttribute(lut_full_kernel<LUT_SUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LutSmem<LUT_SUB>));
-            if (e != cudaSuccess) return check_cuda(ctx, e, "lut_full_kernel shared memory");
-            ctx->lut_attr_set = 1;
-        }
-        lut_full_kernel<1><<<n_sets, LUT_CTA, sizeof(LutSmem<1>), s>>>(n_sets, cap, structure, lut);
-        lut_full_kernel<LUT_SUB><<<n_sets, LUT_CTA, sizeof(LutSmem<LUT_SUB>), s>>>(n_sets, cap, structure, lut);
-        kopen_kernel<<<(unsigned) (((long) n_sets * 32 + 127) / 128), 128, 0, s>>>(n_sets, lut);
-        ctx->launches += 2;
+    if (method == GORT_LUT_Q08) {
+        lut_q08_kernel<<<n_sets, LUT_THREADS, 0, s>>>(n_sets, structure, lut);
+        ctx->launches++;
+        return check_cuda(ctx, cudaGetLastError(), "gort_lut launch");
     }
+    // group cap: as large as possible (the geometry is shared by the whole group) while the batch still yields
+    // enough groups to fill the GPU a few times over; results do not depend on it
+    int cap = n_sets / (ctx->sm_count * 12);
+    if (cap < 1) cap = 1;
+    if (cap > LUT_GROUP_CAP) cap = LUT_GROUP_CAP;
+    if (!ctx->lut_attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(lut_crown_kernel<LUT_SUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(CrownSmem<LUT_SUB>));
+        if (e != cudaSuccess) return check_cuda(ctx, e, "lut_crown_kernel shared memory");
+        ctx->lut_attr_set = 1;
+    }
+    const int chunk = n_sets < LUT_CHUNK ? n_sets : LUT_CHUNK;
+    // workspace of one pass
+    const size_t per_set = sizeof(double) * (4 + GORT_NLAYERS + LUT_NSP) * LUT_ZW + 2 * sizeof(int);
+    char *base = (char *) workspace(ctx, per_set * (size_t) chunk + 256);
+    if (!base) return GORT_ERR_NOMEM;
+    LutWork w;
+    w.trig = (double *) base;
+    w.vg = w.trig + (size_t) chunk * 4 * LUT_ZW;
+    w.tube = w.vg + (size_t) chunk * GORT_NLAYERS * LUT_ZW;
+    w.head = (int *) (w.tube + (size_t) chunk * LUT_NSP * LUT_ZW);
+    w.sub = w.head + chunk;
+    const size_t N = (size_t) n_sets;
+    for (int m0 = 0; m0 < n_sets; m0 += chunk) {
+        const int n = n_sets - m0 < chunk ? n_sets - m0 : chunk;
+        lut_plan_kernel<<<(n + 127) / 128, 128, 0, s>>>(n, m0, cap, structure, N, w);
+        lut_prep_kernel<<<(unsigned) (((long) n * LUT_ZW + 127) / 128), 128, 0, s>>>(n, m0, structure, N, w);
+        lut_vg_kernel<<<(unsigned) (((long) n * LUT_ZW + LUT_VG_THREADS - 1) / LUT_VG_THREADS), LUT_VG_THREADS, 0, s>>>(n, m0, structure, N, w);
+        lut_tube_kernel<<<dim3((unsigned) n, 3), 32 * LUT_NSP, 0, s>>>(n, m0, structure, N, w);
+        lut_crown_kernel<1><<<dim3((unsigned) n, 3), 32 * LUT_NSP, sizeof(CrownSmem<1>), s>>>(n, m0, structure, N, w, lut);
+        lut_crown_kernel<LUT_SUB><<<dim3((unsigned) n, 3), 32 * LUT_NSP, sizeof(CrownSmem<LUT_SUB>), s>>>(n, m0, structure, N, w, lut);
+        ctx->launches += 6;
+    }
+    kopen_kernel<<<(unsigned) (((long) n_sets * 32 + 127) / 128), 128, 0, s>>>(n_sets, lut);
     ctx->launches++;
     return check_cuda(ctx, cudaGetLastError(), "gort_lut launch");
 }

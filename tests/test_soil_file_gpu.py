@@ -64,7 +64,8 @@ def test_cli_soil_spectra_runs_the_model_with_the_file(gort, oracle, tmp_path):
     lut = oracle.lut(st)
     rsurf, _, _ = oracle.brdf(st, lut, ang, rl, tl, rs)
     alb, fv, fs = oracle.energy(st, lut, ang, rl, tl, rs)
-    want = np.concatenate([ang, rsurf, alb, fv, fs], axis=1)
+    # line layout: angles, rsurf per band, then (albedo, favegt, fasoil) per band (gortt.c:309-325)
+    want = np.concatenate([ang, rsurf, np.stack([alb, fv, fs], axis=2).reshape(2, -1)], axis=1)
     assert got.shape == want.shape
     assert np.max(np.abs(got - want)) <= 1.000001e-6          # "%f" text: 6 decimals
     # and it differs from the Price soil run: the option is live
