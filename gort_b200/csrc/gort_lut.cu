@@ -107,6 +107,15 @@ __device__ __forceinline__ double sqrt_lite(double x)
     const double y1 = fma(fma(e, 0.375, 0.5), y * e, y);
     return x == 0.0 ? 0.0 : x * y1;
 }
+// the same with the reference's clamp (gortt_pn_kopen.c:867: |a3| < 1e-10 -> 0) folded into the final select
+__device__ __forceinline__ double sqrt_clamped(double x)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double e = fma(x, -(y * y), 1.0);
+    const double y1 = fma(fma(e, 0.375, 0.5), y * e, y);
+    return fabs(x) < 0.0000000001 ? 0.0 : x * y1;
+}
 
 // gortt_pn_kopen.c:858-872, as the reference writes it (used for the two end points)
 __device__ __forceinline__ double triang_fcn(double x, double b, double r, double tan_the)
@@ -136,19 +145,11 @@ __device__ __noinline__ double triang(double b, double r, const Ang& a)
     double sum1 = 0.0, sum2 = 0.0, f = 1.0;
 #pragma unroll 2
     for (int i = 0; i < m - 1; i++, f += 2.0) {
-        double q1 = fma(fma(c2, f, c1), f, c0);
-        if (fabs(q1) < 0.0000000001) q1 = 0.0;
-        sum1 += (d * f) * sqrt_lite(q1);                         // odd points 1, 3, .., 37
+        sum1 += (d * f) * sqrt_clamped(fma(fma(c2, f, c1), f, c0));      // odd points 1, 3, .., 37
         const double g = f + 1.0;
-        double q2 = fma(fma(c2, g, c1), g, c0);
-        if (fabs(q2) < 0.0000000001) q2 = 0.0;
-        sum2 += (d * g) * sqrt_lite(q2);                         // even points 2, 4, .., 38
+        sum2 += (d * g) * sqrt_clamped(fma(fma(c2, g, c1), g, c0));      // even points 2, 4, .., 38
     }
-    {
-        double q1 = fma(fma(c2, f, c1), f, c0);                  // point 39
-        if (fabs(q1) < 0.0000000001) q1 = 0.0;
-        sum1 += (d * f) * sqrt_lite(q1);
-    }
+    sum1 += (d * f) * sqrt_clamped(fma(fma(c2, f, c1), f, c0));          // point 39
     double volume = 4.0 * sum1;
     volume += 2.0 * sum2;
     volume += triang_fcn(x0, b, r, a.t);
@@ -574,33 +575,47 @@ lut_crown_kernel(int n, int m0, const double* __restrict__ structure, size_t N, 
         const double c0 = E / (1.0 - E) * P_s_p;
         const double q = exp(-(es / sp));
         const double spd = sp * (1.0 / S.c.ds), spd5 = spd + 0.5;
+        // Hot loop without branches: the bin comes from the fast form; a crown count whose fast form lands within 1e-9
+        // of a bin boundary, or whose bin lies beyond the table, only raises a flag (and reads a clamped table row).
+        // A flagged (zenith, entry height) -- about one in 10^6 -- is then redone from scratch with the literal formulas.
         double pw = c0, qn = 1.0;
-#pragma unroll 1
+        bool redo = false;
+#pragma unroll 5
         for (int nn = 1; nn <= LUT_MAXCROWNS; nn++) {                            // :489
             pw *= temp1;                                                         // temp1^n e^-t / (1 - e^-t) P(s')
             qn *= q;
             const double wgt = pw * c_inv_fact[nn];
-            double u = fma(-spd, qn, spd5);
-            // nearest integer and floor of u (0 <= u < 2^31) without the conversion unit: adding 1.5 * 2^52 leaves
-            // round-to-nearest(u) in the low word of the sum
-            double v = u + 6755399441055744.0;
-            double dlt = u - (v - 6755399441055744.0);
-            if (fabs(dlt) < 1e-9) {
-                u = sp * (1.0 - exp(-1.0 * (double) nn * es / sp)) / S.c.ds + 0.5;       // the literal formula, :508, :134-139
-                v = u + 6755399441055744.0;
-                dlt = u - (v - 6755399441055744.0);
-            }
-            const int idx = __double2loint(v) - (dlt < 0.0 ? 1 : 0);                       // (int) u
+            const double u = fma(-spd, qn, spd5);
+            const int idx = (int) u;
+            redo |= (fabs(u - rint(u)) < 1e-9) | ((unsigned) idx >= (unsigned) n_tab);
+            const int row = min(max(idx, 0), n_tab - 1);
             // gortt_calc_epgap + gortt_calc_pgap, :1110-1114, :1138
-            if (idx >= 0 && idx < n_tab) {
 #pragma unroll
-                for (int j = 0; j < SUB; j++) e_t[j] = fma(s_tab[j][idx], wgt, e_t[j]);
-            } else {
-                const double sbin = (double) idx * S.c.ds;
+            for (int j = 0; j < SUB; j++) e_t[j] = fma(s_tab[j][row], wgt, e_t[j]);
+        }
+        if (redo) {
 #pragma unroll
-                for (int j = 0; j < SUB; j++) {                                  // beyond the table: the formula itself
-                    const double tau_j = 0.5 * (structure[5 * N + m + (j < nj ? j : 0)] * S.ellip);
-                    e_t[j] = fma(exp(-sbin * tau_j), wgt, e_t[j]);
+            for (int j = 0; j < SUB; j++) e_t[j] = 0.0;
+            pw = c0; qn = 1.0;
+#pragma unroll 1
+            for (int nn = 1; nn <= LUT_MAXCROWNS; nn++) {
+                pw *= temp1;
+                qn *= q;
+                const double wgt = pw * c_inv_fact[nn];
+                double u = fma(-spd, qn, spd5);
+                if (fabs(u - rint(u)) < 1e-9)
+                    u = sp * (1.0 - exp(-1.0 * (double) nn * es / sp)) / S.c.ds + 0.5;   // the literal formula, :508, :134-139
+                const int idx = (int) u;
+                if (idx >= 0 && idx < n_tab) {
+#pragma unroll
+                    for (int j = 0; j < SUB; j++) e_t[j] = fma(s_tab[j][idx], wgt, e_t[j]);
+                } else {
+                    const double sbin = (double) idx * S.c.ds;
+#pragma unroll
+                    for (int j = 0; j < SUB; j++) {                              // beyond the table: the formula itself
+                        const double tau_j = 0.5 * (structure[5 * N + m + (j < nj ? j : 0)] * S.ellip);
+                        e_t[j] = fma(exp(-sbin * tau_j), wgt, e_t[j]);
+                    }
                 }
             }
         }
