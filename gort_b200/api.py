@@ -59,7 +59,7 @@ ABI_SYMBOLS = [
     "gort_prospect_batch", "gort_brdf_batch", "gort_brdf_batch_dev", "gort_energy_batch",
     "gort_energy_batch_dev", "gort_gauleg", "gort_lut_write_text", "gort_lut_read_text",
     "gort_dfma_peak", "gort_profile_begin", "gort_profile_end", "gort_set_overlap",
-    "gort_soil_table_read", "gort_soil_from_table", "gort_soil_from_table_dev",
+    "gort_host_alloc_near", "gort_host_alloc_on_cpus", "gort_host_placement", "gort_soil_table_read", "gort_soil_from_table", "gort_soil_from_table_dev",
 ]
 
 
@@ -88,6 +88,11 @@ def load_library():
     lib.gort_device_count.restype = C.c_int
     lib.gort_host_alloc.argtypes = [C.c_size_t]
     lib.gort_host_alloc.restype = vp
+    lib.gort_host_alloc_on_cpus.argtypes = [C.c_size_t, C.POINTER(C.c_int), C.c_int]
+    lib.gort_host_alloc_on_cpus.restype = vp
+    lib.gort_host_alloc_near.argtypes = [vp, C.c_size_t]
+    lib.gort_host_alloc_near.restype = vp
+    lib.gort_host_placement.argtypes = [vp, C.c_char_p, C.c_size_t]
     lib.gort_host_free.argtypes = [vp]
     lib.gort_host_free.restype = None
     lib.gort_launch_count.argtypes = [vp]
@@ -133,12 +138,19 @@ def _ptr(a):
 
 
 class PinnedArray:
-    """A numpy float64 view over pinned host memory from gort_host_alloc."""
+    """A numpy float64 view over pinned host memory from gort_host_alloc; with cpus=[...] pinned while running on those
+    CPUs (gort_host_alloc_on_cpus); with near=<Gort> placed by that context's own probe (gort_host_alloc_near)."""
 
-    def __init__(self, shape):
+    def __init__(self, shape, near=None, cpus=None):
         self._lib = load_library()
         n = int(np.prod(shape))
-        self._p = self._lib.gort_host_alloc(max(n, 1) * 8)
+        if cpus:
+            arr = (C.c_int * len(cpus))(*[int(c) for c in cpus])
+            self._p = self._lib.gort_host_alloc_on_cpus(max(n, 1) * 8, arr, len(cpus))
+        elif near is not None:
+            self._p = self._lib.gort_host_alloc_near(near._h, max(n, 1) * 8)
+        else:
+            self._p = self._lib.gort_host_alloc(max(n, 1) * 8)
         if not self._p:
             raise GortError(4, "gort_host_alloc failed")
         buf = (C.c_double * n).from_address(self._p)
@@ -195,6 +207,12 @@ class Gort:
     def set_overlap(self, enable=True):
         """Let consecutive same-shape brdf_dev calls overlap on the GPU (contract: include/gort_b200.h)."""
         self._check(self._lib.gort_set_overlap(self._h, int(bool(enable))))
+
+    def host_placement(self):
+        """what gort_host_alloc_near found out about pinned-buffer placement (a sentence)"""
+        buf = C.create_string_buffer(600)
+        self._check(self._lib.gort_host_placement(self._h, buf, 600))
+        return buf.value.decode()
 
     def launch_count(self):
         return self._lib.gort_launch_count(self._h)

