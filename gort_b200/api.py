@@ -59,7 +59,7 @@ ABI_SYMBOLS = [
     "gort_prospect_batch", "gort_brdf_batch", "gort_brdf_batch_dev", "gort_energy_batch",
     "gort_energy_batch_dev", "gort_gauleg", "gort_lut_write_text", "gort_lut_read_text",
     "gort_dfma_peak", "gort_profile_begin", "gort_profile_end", "gort_set_overlap",
-    "gort_host_alloc_near", "gort_host_alloc_on_cpus", "gort_host_placement", "gort_soil_table_read", "gort_soil_from_table", "gort_soil_from_table_dev",
+    "gort_forward_batch", "gort_host_alloc_near", "gort_host_alloc_on_cpus", "gort_host_placement", "gort_soil_table_read", "gort_soil_from_table", "gort_soil_from_table_dev",
 ]
 
 
@@ -107,6 +107,7 @@ def load_library():
     lib.gort_brdf_batch_dev.argtypes = [vp, vp, sp] + [vp] * 9
     lib.gort_energy_batch.argtypes = [vp, sp] + [vp] * 9
     lib.gort_energy_batch_dev.argtypes = [vp, vp, sp] + [vp] * 9
+    lib.gort_forward_batch.argtypes = [vp, sp, C.c_int, vp, vp, vp, C.c_double, C.c_double, vp, vp, vp, vp]
     lib.gort_gauleg.argtypes = [vp, vp, vp]
     lib.gort_lut_write_text.argtypes = [vp, vp]
     lib.gort_lut_write_text.restype = C.c_long
@@ -321,6 +322,26 @@ class Gort:
         if want_kprop:
             res += (kprop,)
         return res if len(res) > 1 else rsurf
+
+    def forward(self, structure, leaf, soil, wavelength, angles, method=LUT_FULL, user_leaf=-1.0, user_soil=-1.0,
+                beta=None, fd=None, out=None, want_lut=False):
+        """Ensemble forward operator (gort_forward_batch): structure [6][M], leaf [7][M], soil [4][M], wavelength [W],
+        angles [4][G] or [4][M][G] -> rsurf [M][G][W] (+ LUT records [M][184] with want_lut); LUTs and spectra stay
+        on the GPU."""
+        st = _np(structure)
+        M = st.shape[1]
+        leaf = None if leaf is None else _np(leaf)
+        soil = None if soil is None else _np(soil)
+        wl = _np(wavelength).ravel()
+        ang = _np(angles)
+        gps = ang.ndim == 3
+        G, W = ang.shape[-1], wl.shape[0]
+        sh = self._shape(M, G, W, gps, 1, beta, fd)
+        rsurf = out if out is not None else np.empty((M, G, W))
+        lut = np.empty((M, LUT_STRIDE)) if want_lut else None
+        self._check(self._lib.gort_forward_batch(self._h, C.byref(sh), method, _ptr(st), _ptr(leaf), _ptr(soil),
+                                                 float(user_leaf), float(user_soil), _ptr(wl), _ptr(ang), _ptr(rsurf), _ptr(lut)))
+        return (rsurf, lut) if want_lut else rsurf
 
     def energy(self, structure, lut, angles, rleaf, tleaf, rsoil, beta=None, fd=None):
         st, lut, ang, rl, tl, rs, M, G, W, gps, sps = self._prep(structure, lut, angles, rleaf, tleaf, rsoil)

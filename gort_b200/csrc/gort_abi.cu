@@ -139,6 +139,7 @@ void gort_destroy(gort_ctx *ctx)
     if (ctx->d_prospect) cudaFree(ctx->d_prospect);
     if (ctx->d_soil) cudaFree(ctx->d_soil);
     if (ctx->prof_ev) { for (int i = 0; i < 3 * ctx->prof_cap; i++) cudaEventDestroy(ctx->prof_ev[i]); free(ctx->prof_ev); }
+    if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); for (int i = 0; i < 6; i++) if (ctx->fwd_ev[i]) cudaEventDestroy(ctx->fwd_ev[i]); cudaStreamDestroy(ctx->copy_stream); }
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     free(ctx);
 }
@@ -513,6 +514,89 @@ int gort_brdf_batch(gort_ctx *ctx, const gort_shape *shape, const double *struct
     TRY(d2h(ctx, scomp, d_scomp, 4 * nl * hp));
     TRY(d2h(ctx, kprop, d_kprop, 4 * nl));
     TRY(check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "gort_brdf_batch"));
+    return check_pipeline_fault(ctx);
+}
+
+// ---- ensemble forward operator: LUT -> spectra -> BRDF, chunked, copies under kernels -------------------
+static int copy_rows(gort_ctx *ctx, cudaStream_t s, double *dst, size_t dst_pitch, const double *src, size_t src_pitch,
+                     size_t width, int rows, cudaMemcpyKind kind, const char *what)
+{
+    // `rows` rows of `width` doubles; pitches in doubles
+    return check_cuda(ctx, cudaMemcpy2DAsync(dst, dst_pitch * sizeof(double), src, src_pitch * sizeof(double),
+                                             width * sizeof(double), (size_t) rows, kind, s), what);
+}
+
+int gort_forward_batch(gort_ctx *ctx, const gort_shape *shape, int lut_method, const double *structure,
+                       const double *leaf, const double *soil, double user_leaf, double user_soil,
+                       const double *wavelength, const double *angles, double *rsurf, double *lut_out)
+{
+    if (!ctx) return GORT_ERR_INVALID;
+    TRY(check_shape(ctx, shape, "gort_forward_batch"));
+    if (!structure || !wavelength || !angles || !rsurf || (user_leaf < 0.0 && !leaf) || (user_soil < 0.0 && !soil))
+        return set_error(ctx, GORT_ERR_INVALID, "gort_forward_batch: NULL argument");
+    if (lut_method != GORT_LUT_FULL && lut_method != GORT_LUT_Q08)
+        return set_error(ctx, GORT_ERR_INVALID, "gort_forward_batch: unknown LUT method %d", lut_method);
+    const size_t M = shape->n_sets, G = shape->n_geom, W = shape->n_wl;
+    for (size_t i = 0; i < W; i++)
+        if (wavelength[i] < GORT_WL_MIN || wavelength[i] > GORT_WL_MAX)
+            return set_error(ctx, GORT_ERR_RANGE, "wavlength out of range (400-2500)");
+    TRYCUDA(ctx, cudaSetDevice(ctx->device), "cudaSetDevice");
+    if (!ctx->copy_stream) {
+        TRYCUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking), "cudaStreamCreate");
+        for (int i = 0; i < 6; i++) TRYCUDA(ctx, cudaEventCreateWithFlags(&ctx->fwd_ev[i], cudaEventDisableTiming), "cudaEventCreate");
+    }
+    cudaStream_t A = ctx->stream, B = ctx->copy_stream;
+    // chunk: at least 8 per batch when the batch is large, never above 16384 members, at least 1024
+    size_t C = (M + 7) / 8;
+    if (C > 16384) C = 16384;
+    if (C < 1024) C = 1024;
+    if (C > M) C = M;
+    const bool per_set_geom = shape->geom_per_set != 0;
+    // device buffers: slots 0-8 and 9-17 are the two chunk buffers, 18 the wavelengths, 19 shared angles
+    double *d_wl, *d_ang_shared = NULL;
+    TRY(h2d(ctx, 18, wavelength, W, &d_wl));
+    if (!per_set_geom) TRY(h2d(ctx, 19, angles, 4 * G, &d_ang_shared));
+    double *buf[2][9];
+    const size_t sz[9] = {6 * C, 7 * C, 4 * C, per_set_geom ? 4 * C * G : 8, C * GORT_LUT_STRIDE, C * W, C * W, C * W, C * G * W};
+    for (int b = 0; b < 2; b++)
+        for (int k = 0; k < 9; k++) {
+            buf[b][k] = (double *) scratch(ctx, 9 * b + k, sz[k] * sizeof(double));
+            if (!buf[b][k]) return GORT_ERR_NOMEM;
+        }
+    // events per buffer: [b] inputs ready (B), [2+b] kernels done (A), [4+b] outputs copied (B)
+    gort_shape sh = *shape;
+    sh.spectra_per_set = 1;
+    sh.out_pitch = 0;
+    int chunk_no = 0;
+    for (size_t m0 = 0; m0 < M; m0 += C, chunk_no++) {
+        const size_t c = M - m0 < C ? M - m0 : C;
+        const int b = chunk_no & 1;
+        // -- stream B: inputs of this chunk (after the kernels that last read this buffer's inputs) --
+        if (chunk_no >= 2) TRYCUDA(ctx, cudaStreamWaitEvent(B, ctx->fwd_ev[2 + b], 0), "cudaStreamWaitEvent");
+        TRY(copy_rows(ctx, B, buf[b][0], c, structure + m0, M, c, 6, cudaMemcpyHostToDevice, "forward: structure"));
+        if (user_leaf < 0.0) TRY(copy_rows(ctx, B, buf[b][1], c, leaf + m0, M, c, 7, cudaMemcpyHostToDevice, "forward: leaf"));
+        if (user_soil < 0.0) TRY(copy_rows(ctx, B, buf[b][2], c, soil + m0, M, c, 4, cudaMemcpyHostToDevice, "forward: soil"));
+        if (per_set_geom) TRY(copy_rows(ctx, B, buf[b][3], c * G, angles + m0 * G, M * G, c * G, 4, cudaMemcpyHostToDevice, "forward: angles"));
+        TRYCUDA(ctx, cudaEventRecord(ctx->fwd_ev[b], B), "cudaEventRecord");
+        // -- stream A: kernels (after the inputs are in, and after the previous outputs of this buffer have left) --
+        TRYCUDA(ctx, cudaStreamWaitEvent(A, ctx->fwd_ev[b], 0), "cudaStreamWaitEvent");
+        if (chunk_no >= 2) TRYCUDA(ctx, cudaStreamWaitEvent(A, ctx->fwd_ev[4 + b], 0), "cudaStreamWaitEvent");
+        sh.n_sets = (int) c;
+        TRY(launch_lut(ctx, A, (int) c, buf[b][0], lut_method, buf[b][4]));
+        TRY(launch_spectra(ctx, A, (int) c, user_leaf < 0.0 ? buf[b][1] : NULL, user_soil < 0.0 ? buf[b][2] : NULL, user_leaf, user_soil,
+                           (int) W, d_wl, buf[b][5], buf[b][6], buf[b][7]));
+        TRY(launch_brdf(ctx, A, sh, buf[b][0], buf[b][4], per_set_geom ? buf[b][3] : d_ang_shared, buf[b][5], buf[b][6], buf[b][7],
+                        buf[b][8], NULL, NULL));
+        TRYCUDA(ctx, cudaEventRecord(ctx->fwd_ev[2 + b], A), "cudaEventRecord");
+        // -- stream B: results of this chunk --
+        TRYCUDA(ctx, cudaStreamWaitEvent(B, ctx->fwd_ev[2 + b], 0), "cudaStreamWaitEvent");
+        TRYCUDA(ctx, cudaMemcpyAsync(rsurf + m0 * G * W, buf[b][8], c * G * W * sizeof(double), cudaMemcpyDeviceToHost, B), "forward: rsurf");
+        if (lut_out) TRYCUDA(ctx, cudaMemcpyAsync(lut_out + m0 * GORT_LUT_STRIDE, buf[b][4], c * GORT_LUT_STRIDE * sizeof(double), cudaMemcpyDeviceToHost, B), "forward: lut");
+        TRYCUDA(ctx, cudaEventRecord(ctx->fwd_ev[4 + b], B), "cudaEventRecord");
+    }
+    TRYCUDA(ctx, cudaStreamSynchronize(B), "gort_forward_batch");
+    TRYCUDA(ctx, cudaStreamSynchronize(A), "gort_forward_batch");
+    note_other_work(ctx);
     return check_pipeline_fault(ctx);
 }
 

@@ -5,12 +5,14 @@
 #include <stddef.h>
 #include "../../include/gort_b200.h"
 
-#define GORT_NSCRATCH 16
+#define GORT_NSCRATCH 32
 #define GORT_MAX_WIDE_CTAS 8192
 
 struct gort_ctx {
     int device;
     cudaStream_t stream;
+    cudaStream_t copy_stream;          // second stream of gort_forward_batch (copies under kernels)
+    cudaEvent_t fwd_ev[6];             // its per-buffer events: inputs ready, kernels done, outputs copied (x2)
     char err[512];
     long launches;
     int sm_count;

@@ -176,6 +176,17 @@ int gort_brdf_batch_dev(gort_ctx *ctx, void *stream, const gort_shape *shape,
                         const double *rleaf, const double *tleaf, const double *rsoil,
                         double *rsurf, double *scomp, double *kprop);
 
+/* ---- forward operator for an ensemble: replaces the body of main for M members at once (gortt.c:108-120 gap
+ *      probabilities, :224-227 spectra, :232-329 the per-line block) with everything but the inputs and rsurf staying
+ *      on the GPU: the data-assimilation use case (BASELINE.json config 4).  Host pointers.
+ *      structure [6][M]; leaf [7][M] / soil [4][M] (NULL when user_leaf / user_soil >= 0); wavelength [W];
+ *      angles [4][G] or [4][M][G] per shape->geom_per_set; shape->spectra_per_set is ignored (spectra are per member).
+ *      rsurf [M][G][W] dense; lut_out (optional, may be NULL) receives the LUT records [M][GORT_LUT_STRIDE].
+ *      Members are processed in chunks on two streams: the copies of one chunk run under the kernels of the next. */
+int gort_forward_batch(gort_ctx *ctx, const gort_shape *shape, int lut_method, const double *structure,
+                       const double *leaf, const double *soil, double user_leaf, double user_soil,
+                       const double *wavelength, const double *angles, double *rsurf, double *lut_out);
+
 /* ---- energy balance: replaces gortt_energy / gortt_albedo / gauleg (include/gortt.h:273-275;
  *      gortt.c:208-209, :322).  One result per input line (only sza/saa of the line matter):
  *      albedo, favegt, fasoil are [M][G][W]. ---------------------------------------------- */

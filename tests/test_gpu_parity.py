@@ -556,3 +556,29 @@ def test_wide_kernel_many_lines_multiwave_geometry(gort, oracle):
         idx = np.arange(0, G, 2999)
         r_o, _, _ = oracle.brdf(st[:, m], lut[m], ang[:, idx].T, rl[m], tl[m], rs[m])
         assert_close(full[m, idx], r_o, "set %d" % m)
+
+
+def test_forward_batch_equals_the_three_calls(gort):
+    """gort_forward_batch (chunked: LUT -> spectra -> BRDF on the GPU, copies under kernels) returns the bits of
+    gort_lut_batch + gort_spectra_batch + gort_brdf_batch; several chunks, ragged last chunk, both angle layouts."""
+    w = wk.c4_enkf(n_members=5003, seed=77)
+    st, ang, wl = w["structure"], w["angles"], w["wavelength"]
+    lut = gort.lut(st)
+    rl, tl, rs = gort.spectra(w["leaf"], w["soil"], wl)
+    want = gort.brdf(st, lut, ang, rl, tl, rs)
+    got, lut2 = gort.forward(st, w["leaf"], w["soil"], wl, ang, want_lut=True)
+    assert np.array_equal(got, want, equal_nan=True) and np.array_equal(lut2, lut, equal_nan=True)
+    # shared geometry, options, -alb_leaf / -alb_soil style overrides
+    shared = np.ascontiguousarray(ang[:, 0, :])
+    want = gort.brdf(st, lut, shared, *gort.spectra(None, w["soil"], wl, user_leaf=0.4), beta=0.3, fd=0.7)
+    got = gort.forward(st, None, w["soil"], wl, shared, user_leaf=0.4, beta=0.3, fd=0.7)
+    assert np.array_equal(got, want, equal_nan=True)
+    # a batch smaller than one chunk, Q08 LUTs
+    small = np.ascontiguousarray(st[:, :7])
+    lq = gort.lut(small, gort_b200.LUT_Q08)
+    sp = gort.spectra(w["leaf"][:, :7], w["soil"][:, :7], wl)
+    assert np.array_equal(gort.forward(small, w["leaf"][:, :7], w["soil"][:, :7], wl, shared, method=gort_b200.LUT_Q08),
+                          gort.brdf(small, lq, shared, *sp), equal_nan=True)
+    with pytest.raises(gort_b200.GortError) as ei:
+        gort.forward(small, w["leaf"][:, :7], w["soil"][:, :7], np.array([399.0, 500.0]), shared)
+    assert ei.value.code == 3
