@@ -59,7 +59,7 @@ ABI_SYMBOLS = [
     "gort_prospect_batch", "gort_brdf_batch", "gort_brdf_batch_dev", "gort_energy_batch",
     "gort_energy_batch_dev", "gort_gauleg", "gort_lut_write_text", "gort_lut_read_text",
     "gort_dfma_peak", "gort_profile_begin", "gort_profile_end", "gort_set_overlap",
-    "gort_forward_batch", "gort_host_alloc_near", "gort_host_alloc_on_cpus", "gort_host_placement", "gort_soil_table_read", "gort_soil_from_table", "gort_soil_from_table_dev",
+    "gort_forward_batch", "gort_lut_intermediates_batch", "gort_lut_intermediates_batch_dev", "gort_host_alloc_near", "gort_host_alloc_on_cpus", "gort_host_placement", "gort_soil_table_read", "gort_soil_from_table", "gort_soil_from_table_dev",
 ]
 
 
@@ -99,6 +99,8 @@ def load_library():
     lib.gort_launch_count.restype = C.c_long
     lib.gort_lut_batch.argtypes = [vp, C.c_int, vp, C.c_int, vp]
     lib.gort_lut_batch_dev.argtypes = [vp, vp, C.c_int, vp, C.c_int, vp]
+    lib.gort_lut_intermediates_batch.argtypes = [vp, C.c_int] + [vp] * 7
+    lib.gort_lut_intermediates_batch_dev.argtypes = [vp, vp, C.c_int] + [vp] * 7
     lib.gort_spectra_batch.argtypes = [vp, C.c_int, vp, vp, C.c_double, C.c_double, C.c_int, vp, vp, vp, vp]
     lib.gort_spectra_batch_dev.argtypes = [vp, vp, C.c_int, vp, vp, C.c_double, C.c_double, C.c_int, vp, vp, vp, vp]
     lib.gort_prospect_batch.argtypes = [vp, C.c_int, vp, vp, vp]
@@ -259,6 +261,22 @@ class Gort:
         out = np.empty((M, LUT_STRIDE))
         self._check(self._lib.gort_lut_batch(self._h, M, _ptr(st), method, _ptr(out)))
         return out
+
+    def lut_intermediates(self, structure):
+        """The intermediates the BRDF never reads (gortt_calc_vb / _fb / _t_open, dk_open, k_open[h]): dict of arrays
+        vb [M][15], fb [M][15][91], t_open / dt_open [M][15][15], dk_open / k_open [M][15]."""
+        st = _np(structure)
+        M = st.shape[1]
+        out = dict(vb=np.empty((M, 15)), fb=np.empty((M, 15, NTH)), t_open=np.empty((M, 15, 15)),
+                   dt_open=np.empty((M, 15, 15)), dk_open=np.empty((M, 15)), k_open=np.empty((M, 15)))
+        self._check(self._lib.gort_lut_intermediates_batch(self._h, M, _ptr(st), *[_ptr(out[k]) for k in
+                                                           ("vb", "fb", "t_open", "dt_open", "dk_open", "k_open")]))
+        return out
+
+    def lut_intermediates_dev(self, structure, vb=None, fb=None, t_open=None, dt_open=None, dk_open=None, k_open=None, stream=None):
+        M = structure.shape[1]
+        self._check(self._lib.gort_lut_intermediates_batch_dev(self._h, stream, M, _ptr(structure), _ptr(vb), _ptr(fb),
+                                                               _ptr(t_open), _ptr(dt_open), _ptr(dk_open), _ptr(k_open)))
 
     def spectra(self, leaf, soil, wavelength, user_leaf=-1.0, user_soil=-1.0, n_sets=None):
         """leaf [7][M], soil [4][M], wavelength [W] -> rleaf, tleaf, rsoil each [M][W]."""

@@ -330,6 +330,32 @@ int gort_lut_batch(gort_ctx *ctx, int n_sets, const double *structure, int metho
     return check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "gort_lut_batch");
 }
 
+int gort_lut_intermediates_batch_dev(gort_ctx *ctx, void *stream, int n_sets, const double *structure, double *vb,
+                                     double *fb, double *t_open, double *dt_open, double *dk_open, double *k_open)
+{
+    if (!ctx) return GORT_ERR_INVALID;
+    if (!structure || n_sets <= 0) return set_error(ctx, GORT_ERR_INVALID, "gort_lut_intermediates_batch: bad arguments");
+    TRYCUDA(ctx, cudaSetDevice(ctx->device), "cudaSetDevice");
+    return launch_lut_dead(ctx, pick(ctx, stream), n_sets, structure, vb, fb, t_open, dt_open, dk_open, k_open);
+}
+
+int gort_lut_intermediates_batch(gort_ctx *ctx, int n_sets, const double *structure, double *vb, double *fb,
+                                 double *t_open, double *dt_open, double *dk_open, double *k_open)
+{
+    if (!ctx) return GORT_ERR_INVALID;
+    if (!structure || n_sets <= 0) return set_error(ctx, GORT_ERR_INVALID, "gort_lut_intermediates_batch: bad arguments");
+    TRYCUDA(ctx, cudaSetDevice(ctx->device), "cudaSetDevice");
+    const size_t M = n_sets;
+    double *d_st, *d[6];
+    double *h[6] = {vb, fb, t_open, dt_open, dk_open, k_open};
+    const size_t sz[6] = {M * 15, M * 15 * GORT_NTH, M * 225, M * 225, M * 15, M * 15};
+    TRY(h2d(ctx, 0, structure, 6 * M, &d_st));
+    for (int k = 0; k < 6; k++) TRY(dout(ctx, 1 + k, h[k], sz[k], &d[k]));
+    TRY(gort_lut_intermediates_batch_dev(ctx, NULL, n_sets, d_st, d[0], d[1], d[2], d[3], d[4], d[5]));
+    for (int k = 0; k < 6; k++) TRY(d2h(ctx, h[k], d[k], sz[k]));
+    return check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "gort_lut_intermediates_batch");
+}
+
 // ---- spectra ------------------------------------------------------------------------------------
 int gort_spectra_batch_dev(gort_ctx *ctx, void *stream, int n_sets, const double *leaf, const double *soil,
                            double user_leaf, double user_soil, int n_wl, const double *wavelength,

@@ -359,6 +359,7 @@ struct LutWork {
     double *trig;       // [n][4][LUT_ZW]    sin, cos, tan of theta', E[S]
     double *vg;         // [n][15][LUT_ZW]   v_g[h][t]
     double *tube;       // [n][13][LUT_ZW]   tube-volume difference per entry height
+    double *es_all;     // [n][15][LUT_ZW]   E[S] towards every layer (only the intermediates path, launch_lut_dead)
 };
 
 __device__ __forceinline__ bool same_shape(const double* __restrict__ st, size_t n, int a, int b)
@@ -636,6 +637,142 @@ lut_crown_kernel(int n, int m0, const double* __restrict__ structure, size_t N, 
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// The intermediates of gortt_gap_probabilities that never reach the BRDF: gortt_calc_vb
+// (gortt_pn_kopen.c:925-972), gortt_calc_fb (:975-1006), gortt_calc_t_open (:1010-1078) and the dk_open / k_open[h] rows of
+// gortt_calc_kopen (:351-375).  gortt_calc_t_open is ~90 % of the reference's LUT time: a z x h x zenith x crown-count
+// nest (15 x 15 x 91 x 30) that re-integrates E[S] (gortt_get_es, a 20-step sum) inside its innermost loop.  Here E[S]
+// towards every layer is tabulated first (lut_es_all_kernel, once per crown shape), and the nest runs with
+// warp = (z, h) pair, lanes = zeniths, exp(-n x) advanced as q^n and temp1^n by multiplication, the zenith sum as a
+// lane-strided sum + shuffle tree (the reference adds the 91 zeniths left to right: same terms, different association).
+__global__ void __launch_bounds__(128)
+lut_es_all_kernel(int n, int m0, const double* __restrict__ structure, size_t N, LutWork w)
+{
+    const long e = (long) blockIdx.x * blockDim.x + threadIdx.x;
+    const int t = (int) (e % LUT_ZW);
+    const int z = (int) ((e / LUT_ZW) % GORT_NLAYERS);
+    const int i = (int) (e / ((long) LUT_ZW * GORT_NLAYERS));
+    if (i >= n || w.head[i] != i || t >= GORT_NTH) return;
+    const Shape S = shape_load(structure, N, m0 + i);
+    const Ang a = ang_load(w, i, t);
+    w.es_all[((size_t) i * GORT_NLAYERS + z) * LUT_ZW + t] = expected_single_crown_path(S.c, a, layer_height_p(S, z));   // gortt_get_es(p, z, t)
+}
+
+struct DeadOut { double *vb, *fb, *t_open, *dt_open, *dk_open, *k_open; };
+
+#define LUT_DEAD_WARPS GORT_NLAYERS
+__global__ void __launch_bounds__(32 * LUT_DEAD_WARPS, 2)
+lut_dead_kernel(int n, int m0, const double* __restrict__ structure, size_t N, LutWork w, DeadOut o)
+{
+    __shared__ double s_vb[GORT_NLAYERS], s_hp[GORT_NLAYERS];
+    __shared__ double s_sin2[LUT_ZW], s_cos[LUT_ZW];
+    __shared__ double s_f1[GORT_NLAYERS][LUT_ZW];          // p_n0[h][t] sin(2 theta_t)
+    const int i = blockIdx.x, m = m0 + i, hd = w.head[i];
+    const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+    const Shape S = shape_load(structure, N, m);
+    const double lambda = structure[0 * N + m], favd = structure[5 * N + m];
+    const double lv_p = (lambda / (S.h2 - S.h1)) * S.ellip;                       // gortt.c:671, :677
+    const double tau_p = 0.5 * (favd * S.ellip);                                  // :675-676
+    const double dth = 1 * GORT_PI / 180.0;
+    const double r = S.c.r;
+    if (threadIdx.x < GORT_NLAYERS) {
+        // gortt_calc_vb, :938-970: sphere centred at layer height, cut by the h1 and h2 planes
+        const double hp = layer_height_p(S, threadIdx.x);
+        double Vol = 4.0 * GORT_PI * S.c.rrr / 3.0, tmp;
+        if (hp + r > S.c.h2_p) { tmp = hp + r - S.c.h2_p; Vol -= GORT_PI * tmp * tmp * (3.0 * r - tmp) / 3.0; }
+        if (hp - r < S.c.h1_p) { tmp = S.c.h1_p - (hp - r); Vol -= GORT_PI * tmp * tmp * (3.0 * r - tmp) / 3.0; }
+        if (Vol < -0.0000001) Vol = __longlong_as_double(0x7ff8000000000000LL);   // the reference exits here: NaN marks the set
+        else if (Vol < 0) Vol = 0.0;
+        s_vb[threadIdx.x] = Vol; s_hp[threadIdx.x] = hp;
+        if (o.vb) o.vb[(size_t) m * GORT_NLAYERS + threadIdx.x] = Vol;
+    }
+    for (int t = threadIdx.x; t < LUT_ZW; t += blockDim.x) {
+        double theta = dth * (double) min(t, GORT_NTH - 1);                       // gortt.c:783-787
+        if (theta >= GORT_PI / 2.0) theta = GORT_PI / 2.0 - 1.0 * GORT_PI / 180.0;
+        s_sin2[t] = sin(2.0 * theta);
+        s_cos[t] = w.trig[(size_t) hd * 4 * LUT_ZW + 1 * LUT_ZW + min(t, GORT_NTH - 1)];
+    }
+    __syncthreads();
+    // ---- p_n0[h][t] for every layer: fb (:981-1003) and the integrands of k_open[h] / dk_open[h] ----
+    {
+        const int h = wp;
+        const double one_m_e = 1.0 - exp(-lv_p * s_vb[h]);
+        for (int t = lane; t < GORT_NTH; t += 32) {
+            const double pn0 = exp(-1.0 * lv_p * w.vg[((size_t) hd * GORT_NLAYERS + h) * LUT_ZW + t]);
+            s_f1[h][t] = pn0;
+            double d = 1.0 - pn0;
+            if (d < 2.2250738585072014e-308 * 2.) d = 2.2250738585072014e-308 * 2.;       // DBL_MIN * 2, :990
+            if (o.fb) o.fb[((size_t) m * GORT_NLAYERS + h) * GORT_NTH + t] = one_m_e / d;
+        }
+    }
+    __syncthreads();
+    {
+        // gortt_calc_kopen, :351-375: trapezoid panels over the zeniths for layer h = warp
+        const int h = wp;
+        double ko = 0.0, dk = 0.0;
+        for (int t = 1 + lane; t < GORT_NTH; t += 32) {
+            const double p1 = s_f1[h][t], p0 = s_f1[h][t - 1];
+            ko += (p1 * s_sin2[t] + p0 * s_sin2[t - 1]) / 2.0 * dth;
+            const double q1 = h == GORT_NLAYERS - 1 ? 0.0 : s_f1[h + 1][t] - p1;          // p_s0, :40-45
+            const double q0 = h == GORT_NLAYERS - 1 ? 0.0 : s_f1[h + 1][t - 1] - p0;
+            dk += (q1 * s_sin2[t] + q0 * s_sin2[t - 1]) / 2.0 * dth;
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) { ko += __shfl_xor_sync(0xffffffffu, ko, off); dk += __shfl_xor_sync(0xffffffffu, dk, off); }
+        if (lane == 0) {
+            if (o.k_open) o.k_open[(size_t) m * GORT_NLAYERS + h] = ko;
+            if (o.dk_open) o.dk_open[(size_t) m * GORT_NLAYERS + h] = dk;
+        }
+    }
+    if (!o.t_open && !o.dt_open) return;
+    // ---- gortt_calc_t_open, :1033-1075: 120 (z, h >= z) pairs dealt round-robin to the warps ----
+    for (int pair = wp; pair < GORT_NLAYERS * (GORT_NLAYERS + 1) / 2; pair += LUT_DEAD_WARPS) {
+        int z = 0, rem = pair;
+        while (rem >= GORT_NLAYERS - z) { rem -= GORT_NLAYERS - z; z++; }
+        const int h = z + rem;
+        double Tsum = 0.0, dTsum = 0.0;
+        if (z != h) {
+            const double dsz = (1.0 - exp(lv_p * s_vb[z])) * S.c.dz_p;             // sic: + exponent, :1055
+            const double dhp = fabs(s_hp[z] - s_hp[h]);
+            for (int t = lane; t < GORT_NTH; t += 32) {
+                const double cth = s_cos[t];
+                const double s_p = dhp / cth;                                      // :1047
+                const double es = w.es_all[((size_t) hd * GORT_NLAYERS + z) * LUT_ZW + t];
+                const double temp1 = lv_p * GORT_PI * r * r * s_p;                 // :1051
+                const double E = exp(-temp1);
+                const double c0 = E / (1.0 - E);
+                const double q = exp(-(es / s_p));
+                const double fac = 1.0 - exp(tau_p * (dsz / cth));                 // :1056
+                double pw = 1.0, qn = 1.0, T = 0.0, dT = 0.0;
+#pragma unroll 2
+                for (int nn = 1; nn <= LUT_MAXCROWNS; nn++) {
+                    pw *= temp1; qn *= q;
+                    const double s = s_p * (1.0 - qn);                             // :1050
+                    const double P_n = pw * c0 * c_inv_fact[nn];                   // :1052-1053
+                    const double pe = P_n * exp(-s * tau_p);
+                    T += pe;                                                       // :1054
+                    dT += pe * fac;                                                // :1056
+                }
+                Tsum += s_sin2[t] * T * dth;                                       // :1059
+                dTsum += s_sin2[t] * dT * dth;
+            }
+        } else {
+            const double dsz = 0.5 * (1.0 - exp(-lv_p * s_vb[z])) * S.c.dz_p;      // :1070
+            for (int t = lane; t < GORT_NTH; t += 32) {
+                const double dT = 1.0 - exp(-tau_p * (dsz / s_cos[t]));
+                dTsum += s_sin2[t] * dT * dth;                                     // :1072
+            }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) { Tsum += __shfl_xor_sync(0xffffffffu, Tsum, off); dTsum += __shfl_xor_sync(0xffffffffu, dTsum, off); }
+        if (lane == 0) {
+            const size_t b = (size_t) m * GORT_NLAYERS * GORT_NLAYERS;
+            if (o.t_open) { o.t_open[b + h * GORT_NLAYERS + z] = Tsum; o.t_open[b + z * GORT_NLAYERS + h] = Tsum; }
+            if (o.dt_open) { o.dt_open[b + h * GORT_NLAYERS + z] = dTsum; o.dt_open[b + z * GORT_NLAYERS + h] = dTsum; }
+        }
+    }
+}
+
 // gortt_pn_kopen.c:1144-1200
 __global__ void __launch_bounds__(LUT_THREADS)
 lut_q08_kernel(int n_sets, const double* __restrict__ structure, double* __restrict__ lut)
@@ -716,6 +853,38 @@ kopen_kernel(int n_sets, double* __restrict__ lut)
     if (lane == 0) { o[2 * GORT_NTH] = ko; o[2 * GORT_NTH + 1] = ke; }
 }
 
+int launch_lut_dead(gort_ctx *ctx, cudaStream_t s, int n_sets, const double *structure, double *vb, double *fb,
+                    double *t_open, double *dt_open, double *dk_open, double *k_open)
+{
+    note_other_work(ctx);
+    int cap = n_sets / (ctx->sm_count * 12);
+    if (cap < 1) cap = 1;
+    if (cap > LUT_GROUP_CAP) cap = LUT_GROUP_CAP;
+    const int chunk = n_sets < LUT_CHUNK / 2 ? n_sets : LUT_CHUNK / 2;
+    const size_t per_set = sizeof(double) * (4 + 2 * GORT_NLAYERS + LUT_NSP) * LUT_ZW + 2 * sizeof(int);
+    char *base = (char *) workspace(ctx, per_set * (size_t) chunk + 256);
+    if (!base) return GORT_ERR_NOMEM;
+    LutWork w;
+    w.trig = (double *) base;
+    w.vg = w.trig + (size_t) chunk * 4 * LUT_ZW;
+    w.tube = w.vg + (size_t) chunk * GORT_NLAYERS * LUT_ZW;
+    w.es_all = w.tube + (size_t) chunk * LUT_NSP * LUT_ZW;
+    w.head = (int *) (w.es_all + (size_t) chunk * GORT_NLAYERS * LUT_ZW);
+    w.sub = w.head + chunk;
+    const size_t N = (size_t) n_sets;
+    for (int m0 = 0; m0 < n_sets; m0 += chunk) {
+        const int n = n_sets - m0 < chunk ? n_sets - m0 : chunk;
+        DeadOut o = {vb, fb, t_open, dt_open, dk_open, k_open};
+        lut_plan_kernel<<<(n + 127) / 128, 128, 0, s>>>(n, m0, cap, structure, N, w);
+        lut_prep_kernel<<<(unsigned) (((long) n * LUT_ZW + 127) / 128), 128, 0, s>>>(n, m0, structure, N, w);
+        lut_vg_kernel<<<(unsigned) (((long) n * LUT_ZW + LUT_VG_THREADS - 1) / LUT_VG_THREADS), LUT_VG_THREADS, 0, s>>>(n, m0, structure, N, w);
+        lut_es_all_kernel<<<(unsigned) (((long) n * LUT_ZW * GORT_NLAYERS + 127) / 128), 128, 0, s>>>(n, m0, structure, N, w);
+        lut_dead_kernel<<<(unsigned) n, 32 * LUT_DEAD_WARPS, 0, s>>>(n, m0, structure, N, w, o);
+        ctx->launches += 5;
+    }
+    return check_cuda(ctx, cudaGetLastError(), "gort_lut_intermediates launch");
+}
+
 int launch_lut(gort_ctx *ctx, cudaStream_t s, int n_sets, const double *structure, int method, double *lut)
 {
     note_other_work(ctx);
@@ -743,6 +912,7 @@ int launch_lut(gort_ctx *ctx, cudaStream_t s, int n_sets, const double *structur
     w.trig = (double *) base;
     w.vg = w.trig + (size_t) chunk * 4 * LUT_ZW;
     w.tube = w.vg + (size_t) chunk * GORT_NLAYERS * LUT_ZW;
+    w.es_all = NULL;
     w.head = (int *) (w.tube + (size_t) chunk * LUT_NSP * LUT_ZW);
     w.sub = w.head + chunk;
     const size_t N = (size_t) n_sets;

@@ -127,6 +127,18 @@ int gort_lut_batch(gort_ctx *ctx, int n_sets, const double *structure, int metho
 int gort_lut_batch_dev(gort_ctx *ctx, void *stream, int n_sets, const double *structure,
                        int method, double *lut);
 
+/* ---- the intermediates of gortt_gap_probabilities that never reach the BRDF or albedo path:
+ *      gortt_calc_vb / gortt_calc_fb / gortt_calc_t_open (gortt_pn_kopen.c:925-1078) and the dk_open / k_open[h] rows of
+ *      gortt_calc_kopen (:351-375), for callers of the reference's unfinished LiDAR / energy extensions and for
+ *      "same work as the reference" timings (gortt_calc_t_open is ~90 % of the reference's LUT time).
+ *      Outputs per set, any of which may be NULL: vb [M][15], fb [M][15][91], t_open [M][15][15], dt_open [M][15][15],
+ *      dk_open [M][15], k_open [M][15].  A set on which the reference would exit ("Significant negative volume",
+ *      :964-967) gets NaN in vb.  GORT_LUT_FULL only. */
+int gort_lut_intermediates_batch(gort_ctx *ctx, int n_sets, const double *structure, double *vb, double *fb,
+                                 double *t_open, double *dt_open, double *dk_open, double *k_open);
+int gort_lut_intermediates_batch_dev(gort_ctx *ctx, void *stream, int n_sets, const double *structure, double *vb,
+                                     double *fb, double *t_open, double *dt_open, double *dk_open, double *k_open);
+
 /* ---- spectra: replaces gortt_price_soil + gortt_prospect_interface + prospect_DB_
  *      (include/gortt.h:289-292; gortt.c:224-227).
  *      leaf is [7][M] rows N,Cab,Car,Anth,Cbrown,Cw,Cm; soil is [4][M] rows rsl1..4.

@@ -879,3 +879,91 @@ int gort_oracle_soil_lookup(const double *table, int nw, const double *wl, doubl
     }
     return 0;
 }
+
+/* ---------------------------------------------------------------------------------------
+ * The intermediates of the gap-probability code that never reach the BRDF:
+ * gortt_calc_vb :925-972, gortt_calc_fb :975-1006, gortt_calc_t_open :1010-1078 and the dk_open /
+ * k_open[h] rows of gortt_calc_kopen :351-375.  Outputs: vb[15], fb[15][91], t_open[15][15],
+ * dt_open[15][15], dk_open[15], k_open[15].
+ * ------------------------------------------------------------------------------------- */
+#include <float.h>
+int gort_oracle_lut_dead(const double *st6, double *vb, double *fb, double *t_open, double *dt_open,
+                         double *dk_open, double *k_open)
+{
+    canopy_t c;
+    canopy_init(&c, st6);
+    double *v_g = (double *) malloc(sizeof(double) * NLAY * NTH * 2);
+    double *p_n0 = v_g + NLAY * NTH;
+    double epgap0[NTH], ko0, ke0;
+    gap_probabilities_full(&c, v_g, p_n0, epgap0, &ko0, &ke0);
+
+    for (int i = 0; i < NLAY; i++) {                             /* gortt_calc_vb, :938-970 */
+        double Vol = 4.0 * M_PI * c.rrr / 3.0, tmp;
+        if (c.height_p[i] + c.r > c.h2_p) {
+            tmp = c.height_p[i] + c.r - c.h2_p;
+            Vol -= M_PI * tmp * tmp * (3.0 * c.r - tmp) / 3.0;
+        }
+        if (c.height_p[i] - c.r < c.h1_p) {
+            tmp = c.h1_p - (c.height_p[i] - c.r);
+            Vol -= M_PI * tmp * tmp * (3.0 * c.r - tmp) / 3.0;
+        }
+        if (Vol < -0.0000001) { free(v_g); return 1; }           /* the reference exits here */
+        if (Vol < 0) Vol = 0.0;
+        vb[i] = Vol;
+    }
+    for (int t = 0; t < NTH; t++)                                /* gortt_calc_fb, :981-1003 */
+        for (int i = 0; i < NLAY; i++) {
+            double d = (1.0 - p_n0[i * NTH + t]);
+            if (d < DBL_MIN * 2.) d = DBL_MIN * 2.;
+            fb[i * NTH + t] = (1.0 - exp(-c.lv_p * vb[i])) / d;
+        }
+    for (int i = 0; i < NLAY * NLAY; i++) { t_open[i] = 0.0; dt_open[i] = 0.0; }
+    for (int z = 0; z < NLAY; z++)                               /* gortt_calc_t_open, :1033-1075 */
+        for (int h = NLAY - 1; h >= z; h--) {
+            t_open[h * NLAY + z] = 0.0;
+            dt_open[h * NLAY + z] = 0.0;
+            if (z != h) {
+                for (int t = 0; t < NTH; t++) {
+                    double T = 0.0, dT = 0.0;
+                    double s_p = fabs(c.height_p[z] - c.height_p[h]) / cos(c.theta_p[t]);
+                    for (int n = 1; n <= MAXCROWNS; n++) {
+                        double s = s_p * (1.0 - exp(-n * expected_single_crown_path(&c, z, t) / s_p));
+                        double temp1 = c.lv_p * M_PI * c.r * c.r * s_p;
+                        double P_n = (pow(temp1, (double) n) * exp(-temp1)) / (c.factorial[n] * (1.0 - exp(-temp1)));
+                        T += P_n * exp(-s * c.tau_p);
+                        double ds = (1.0 - exp(c.lv_p * vb[z])) * c.dz_p / cos(c.theta_p[t]);      /* sic: + exponent */
+                        dT += P_n * exp(-s * c.tau_p) * (1.0 - exp(c.tau_p * ds));
+                    }
+                    t_open[h * NLAY + z] += sin(2.0 * c.theta[t]) * T * c.dth;
+                    dt_open[h * NLAY + z] += sin(2.0 * c.theta[t]) * dT * c.dth;
+                    t_open[z * NLAY + h] = t_open[h * NLAY + z];
+                    dt_open[z * NLAY + h] = dt_open[h * NLAY + z];
+                }
+            } else {
+                for (int t = 0; t < NTH; t++) {
+                    double ds = 0.5 * (1.0 - exp(-c.lv_p * vb[z])) * c.dz_p / cos(c.theta_p[t]);
+                    double dT = 1.0 - exp(-c.tau_p * ds);
+                    dt_open[h * NLAY + z] += sin(2.0 * c.theta[t]) * dT * c.dth;
+                }
+            }
+        }
+    for (int h = 0; h < NLAY; h++) {                             /* gortt_calc_kopen, :351-375 */
+        double ko = 0.0, dk = 0.0;
+        double ps_last = (h == NLAY - 1 ? 0.0 : p_n0[(h + 1) * NTH] - p_n0[h * NTH]);
+        double tmp1_last = p_n0[h * NTH] * sin(2.0 * c.theta[0]);
+        double tmp3_last = ps_last * sin(2.0 * c.theta[0]);
+        for (int t = 1; t < NTH; t++) {
+            double tmp1 = p_n0[h * NTH + t] * sin(2.0 * c.theta[t]);
+            ko += (tmp1 + tmp1_last) / 2.0 * c.dth;
+            tmp1_last = tmp1;
+            double ps = (h == NLAY - 1 ? 0.0 : p_n0[(h + 1) * NTH + t] - p_n0[h * NTH + t]);     /* p_s0, :40-45 */
+            double tmp3 = ps * sin(2.0 * c.theta[t]);
+            dk += (tmp3 + tmp3_last) / 2.0 * c.dth;
+            tmp3_last = tmp3;
+        }
+        k_open[h] = ko;
+        dk_open[h] = dk;
+    }
+    free(v_g);
+    return 0;
+}

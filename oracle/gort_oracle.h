@@ -29,6 +29,10 @@ long gort_oracle_brdf_repeat(const double *st6, const double *lut, int ngeom, co
                              const double *rleaf, const double *tleaf, const double *rsoil,
                              int reps, double *rsurf_last);
 
+/* intermediates that never reach the BRDF (gortt_calc_vb / _fb / _t_open, dk_open; gortt_pn_kopen.c:925-1078, :351-375) */
+int gort_oracle_lut_dead(const double *st6, double *vb, double *fb, double *t_open, double *dt_open,
+                         double *dk_open, double *k_open);
+
 /* soil spectrum file (gortt_read_soil_lut, gortt.c:1388-1451) and the 1-nm lookup */
 int gort_oracle_soil_table(const char *path, double *table, double *where);
 int gort_oracle_soil_lookup(const double *table, int nw, const double *wl, double *rsoil);

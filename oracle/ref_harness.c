@@ -112,6 +112,25 @@ int ref_lut_intermediates(const double *st6, double *v_g, double *p_n0, double *
     return 0;
 }
 
+/* The intermediates that never reach the BRDF, straight from the reference's struct after its own
+ * gortt_gap_probabilities: vb[15], fb[15][91], t_open[15][15], dt_open[15][15], dk_open[15], k_open[15]. */
+int ref_lut_dead(const double *st6, double *vb, double *fb, double *t_open, double *dt_open,
+                 double *dk_open, double *k_open)
+{
+    gortt_parameters p; gortt_geometry g;
+    ref_defaults(&p, &g);
+    ref_set_structure(&p, st6);
+    gortt_init_params(&p, &g);
+    gortt_gap_probabilities(&p, &g);
+    for (int h = 0; h < 15; h++) {
+        vb[h] = p.vb[h]; dk_open[h] = p.dk_open[h]; k_open[h] = p.k_open[h];
+        for (int t = 0; t < REF_NTH; t++) fb[h * REF_NTH + t] = p.fb[h][t];
+        for (int z = 0; z < 15; z++) { t_open[h * 15 + z] = p.t_open[h][z]; dt_open[h * 15 + z] = p.dt_open[h][z]; }
+    }
+    ref_free_params(&p);
+    return 0;
+}
+
 /* Fill a reference parameter struct from structure + a LUT record (as "-P" does, gortt.c:131-146). */
 static void ref_params_with_lut(gortt_parameters *p, gortt_geometry *g, const double *st6,
                                 const double *lut, const double *opt)

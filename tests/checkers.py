@@ -100,6 +100,17 @@ class Checker:
         self._spectra(_p(leaf7), _p(soil4), user_leaf, user_soil, nw, _p(wl), _p(rl), _p(tl), _p(rs))
         return rl, tl, rs
 
+    def lut_dead(self, st6):
+        """vb[15], fb[15][91], t_open[15][15], dt_open[15][15], dk_open[15], k_open[15] (gortt_pn_kopen.c:925-1078)."""
+        fn = getattr(self.lib, self.prefix + "lut_dead")
+        fn.argtypes = [_dp] * 7
+        fn.restype = C.c_int
+        out = dict(vb=np.empty(15), fb=np.empty((15, NTH)), t_open=np.empty((15, 15)), dt_open=np.empty((15, 15)),
+                   dk_open=np.empty(15), k_open=np.empty(15))
+        rc = fn(_p(self._st(st6)), *[_p(out[k]) for k in ("vb", "fb", "t_open", "dt_open", "dk_open", "k_open")])
+        assert rc == 0, "negative sphere volume: the reference exits on this structure"
+        return out
+
     def soil_table(self, path):
         """(restatement only) -> (rc, table[2101], where): the reference's soil-file interpolation loop."""
         fn = self.lib.gort_oracle_soil_table

@@ -160,3 +160,14 @@ def test_ulp_sensitivity_harness(oracle):
     s = sensitivity(lambda c: c.lut(st), lut)
     rel = s / np.maximum(np.abs(lut), 1e-12)
     assert 0 < rel.max() < 1e-9
+
+
+def test_dead_intermediates_restatement_vs_live_reference(oracle, ref):
+    """vb / fb / t_open / dt_open / dk_open / k_open[h] (gortt_pn_kopen.c:925-1078, :351-375): the restatement equals the
+    compiled reference bit for bit."""
+    rng = np.random.Generator(np.random.PCG64(808))
+    st = wk.random_structures(rng, 4)
+    for m in range(4):
+        a, b = oracle.lut_dead(st[:, m]), ref.lut_dead(st[:, m])
+        for k in a:
+            assert same(a[k], b[k]), "%s, structure %d" % (k, m)
