@@ -661,6 +661,11 @@ def extras(g, torch, dev, ts, near_cpus=None):
     d_lut = E(M, LUT_STRIDE); d_rl, d_tl, d_rs = E(M, W), E(M, W), E(M, W)
     lut_ms = _time_dev(torch, ts, lambda: g.lut_dev(d_st, d_lut, stream=stream))
     sp_ms = _time_dev(torch, ts, lambda: g.spectra_dev(d_leaf, d_soil, d_wl, d_rl, d_tl, d_rs, stream=stream))
+    # the same sets with the intermediates the reference also computes (vb, fb, t_open, dt_open, dk_open: ~90 % of its
+    # LUT time, never read by the BRDF): "same work as the reference"
+    d_int = [E(M, k) for k in (15, 15 * 91, 225, 225, 15, 15)]
+    int_ms = _time_dev(torch, ts, lambda: g.lut_intermediates_dev(d_st, *d_int, stream=stream), reps=2)
+    del d_int
     d_a, d_v, d_s = E(M, S, W), E(M, S, W), E(M, S, W)
     en_ms = _time_dev(torch, ts, lambda: g.energy_dev(d_st, d_lut, d_ang, d_rl, d_tl, d_rs, d_a, d_v, d_s, stream=stream))
     evals = M * S * 512 * W
@@ -671,6 +676,10 @@ def extras(g, torch, dev, ts, near_cpus=None):
                                                  "records + 512 W evaluations)",
                         "lut_kernels_ms": lut_ms, "luts_per_s": M / (lut_ms * 1e-3),
                         "lut_fp64": alg(M * F_LUT, lut_ms, "lut_tube_kernel", False),
+                        "lut_intermediates_ms": int_ms,
+                        "luts_per_s_same_work_as_reference": M / ((lut_ms + int_ms) * 1e-3),
+                        "lut_same_work_note": "outputs (lut_kernels_ms) + the intermediates the reference computes on every run and the "
+                                              "BRDF never reads (gort_lut_intermediates_batch: vb, fb, t_open, dt_open, dk_open)",
                         "spectra_kernel_ms": sp_ms, "spectra_fp64": alg(M * W * 130.0, sp_ms, "spectra_kernel", False),
                         "finite_fraction": float(torch.isfinite(d_a).double().mean())}
     del d_a, d_v, d_s
