@@ -644,15 +644,14 @@ def extras(g, torch, dev, ts, near_cpus=None):
                           "note": "same sweep, lines permuted: every line starts a new run, so the (sun, lambda) terms "
                                   "(2 divisions + ~35 FP64 operations per wavelength) are rebuilt per line instead of once per "
                                   "36 lines and the kernel turns FP64-bound; callers that can should keep lines sharing a sun adjacent"}
-    G4 = G // 4
-    d_ang4 = T(ang[:, :G4])
-    d_r4, d_sc = E(1, G4, Wp), E(1, G4, Wp, 4)
-    sc_ms = _time_dev(torch, ts, lambda: g.brdf_dev(d_st, d_lut, d_ang4, d_rl[0], d_tl[0], d_rs[0], d_r4, scomp=d_sc, stream=stream))
-    res["c2_prnspec"] = {"lines": G4, "wavelengths": W, "brdf_ms": sc_ms, "evals_per_s": G4 * W / (sc_ms * 1e-3),
-                         "roofline": {"bound": "hbm", "achieved": 40.0 * G4 * W / (sc_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
-                                      "frac": 40.0 * G4 * W / (sc_ms * 1e-3) / 1e9 / hbm,
-                                      "note": "geometry kernel + per-wavelength kernel of one isolated call, 40 B per evaluation"}}
-    del d_r, d_r4, d_sc
+    d_sc = E(1, G, Wp, 4)
+    sc_ms = _time_dev(torch, ts, lambda: g.brdf_dev(d_st, d_lut, d_ang, d_rl[0], d_tl[0], d_rs[0], d_r, scomp=d_sc, stream=stream))
+    res["c2_prnspec"] = {"lines": G, "wavelengths": W, "brdf_ms": sc_ms, "evals_per_s": G * W / (sc_ms * 1e-3),
+                         "roofline": {"bound": "hbm", "achieved": 40.0 * G * W / (sc_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                                      "frac": 40.0 * G * W / (sc_ms * 1e-3) / 1e9 / hbm,
+                                      "note": "geometry kernel + per-wavelength kernel of one isolated call over the whole sweep, "
+                                              "40 B per evaluation (rsurf + C, G, T, Z), 980 MB out"}}
+    del d_r, d_sc
 
     # ---- C3: spectral albedo + fAPAR, 10^4 sets x 3 sun angles x 211 bands x 512 quadrature nodes ----
     w = wk.c3_albedo()

@@ -284,8 +284,9 @@ static int launch_wide(gort_ctx *ctx, cudaStream_t s, const gort_shape &sh, cons
     a.done = ctx->d_done; a.fault = ctx->d_done + GORT_MAX_WIDE_CTAS;
     a.tile_flags = pl.flags; a.call_no = ctx->call_no;
     constexpr int STAGE = WIDE_STAGE_LINES;
+    constexpr int RINGW = SCOMP ? 5 : 1;                  // doubles per evaluation in the output ring
     const size_t smem = sizeof(double2) * 8 * STAGE + sizeof(unsigned) * 4
-                      + sizeof(double) * (WIDE_NLEAF + 2 * TMAB) * (size_t) a.chunk;
+                      + sizeof(double) * (WIDE_NLEAF + 2 * TMAB * RINGW) * (size_t) a.chunk;
     auto kern = rsurf_wide_kernel<LPT, SCOMP, MINB, TMAB>;
     // occupancy of this (variant, block size) is looked up once per context
     int occ = 0;
@@ -296,7 +297,7 @@ static int launch_wide(gort_ctx *ctx, cudaStream_t s, const gort_shape &sh, cons
     if (occ == 0) {
         // allow the largest chunk any block size can ask for, so that the attribute never shrinks
         const size_t smem_max = sizeof(double2) * 8 * STAGE + sizeof(unsigned) * 4
-                              + sizeof(double) * (WIDE_NLEAF + 2 * TMAB) * (size_t) LPT * WIDE_MAX_THREADS;
+                              + sizeof(double) * (WIDE_NLEAF + 2 * TMAB * RINGW) * (size_t) LPT * (TMAB > 0 ? WIDE_PICK_THREADS_TMA : WIDE_MAX_THREADS);
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_max);
         if (e != cudaSuccess) return check_cuda(ctx, e, "rsurf_wide_kernel shared memory");
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem);
@@ -550,8 +551,9 @@ int launch_brdf(gort_ctx *ctx, cudaStream_t s, const gort_shape &sh, const doubl
 #define WIDE_ARGS ctx, s, sh, pl, structure, lut, rleaf, tleaf, rsoil, rsurf, scomp
             // Output path: rows through shared memory and TMA bulk stores (3 rows per CTA barrier, LPT = 4) when the
             // rows are 128-byte aligned, else per-thread stores
-            const bool tma = !ctx->dbg_no_tma && pitch % 16 == 0 && ((size_t) rsurf & 15) == 0;
-            if (scomp) rc = launch_wide<2, true, 2, 0>(WIDE_ARGS);
+            const bool tma = !ctx->dbg_no_tma && pitch % 16 == 0 && ((size_t) rsurf & 15) == 0 && ((size_t) scomp & 15) == 0;
+            if (scomp && tma) rc = launch_wide<2, true, 2, WIDE_TMA_ROWS_SCOMP>(WIDE_ARGS);
+            else if (scomp) rc = launch_wide<2, true, 2, 0>(WIDE_ARGS);
             else if (tma) rc = launch_wide<4, false, 2, WIDE_TMA_ROWS>(WIDE_ARGS);
             else if (lpt == 4) rc = launch_wide<4, false, 2, 0>(WIDE_ARGS);
             else if (lpt == 3) rc = launch_wide<3, false, 2, 0>(WIDE_ARGS);

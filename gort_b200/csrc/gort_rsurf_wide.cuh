@@ -49,6 +49,7 @@ namespace gort {
 #define WIDE_PICK_THREADS 288     // largest block the launch heuristic picks: two CTAs then leave an SM room for one geom_kernel CTA
 #define WIDE_PICK_THREADS_TMA 192 // same, TMA output path: (9 + 2*3) arrays of 4*192 doubles + 16 KB of records, twice, fit 227 KB
 #define WIDE_TMA_ROWS 3           // rows per CTA barrier on the TMA output path
+#define WIDE_TMA_ROWS_SCOMP 2     // the same with component signatures (40 B per evaluation in the ring)
 #define WIDE_STAGE_LINES 128      // lines staged in shared memory per pass (16 KB)
 #define WIDE_NLEAF 9              // omega gam Tff Rff pff tff rs Xf A
 
@@ -81,7 +82,7 @@ rsurf_wide_kernel(const WideArgs a)
     double2* srec = smem2;                                                    // [STAGE][8] packed records
     unsigned* runmask = reinterpret_cast<unsigned*>(srec + 8 * STAGE);   // [STAGE / 32] run-start bits (16 bytes reserved)
     double* leaf = reinterpret_cast<double*>(runmask + 4);                 // [WIDE_NLEAF][chunk], 16-byte aligned
-    double* ring = leaf + (size_t) WIDE_NLEAF * a.chunk;                              // TMAB > 0: [2 * TMAB][chunk] output rows
+    double* ring = leaf + (size_t) WIDE_NLEAF * a.chunk;                              // TMAB > 0: two halves of TMAB output rows (x5 with component signatures)
     __shared__ int s_fault;       // a bounded wait expired: this CTA stores nothing more (and the host is told)
     if (threadIdx.x == 0) s_fault = 0;
     __syncthreads();
@@ -286,6 +287,52 @@ rsurf_wide_kernel(const WideArgs a)
                             const unsigned sa = (unsigned) __cvta_generic_to_shared(ring + ((size_t) half * TMAB + b) * chunk);
                             asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                                          :: "l"(a.rsurf + (size_t) (s0 + l + b) * a.pitch + wbase), "r"(sa), "r"(row_bytes) : "memory");
+                        }
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                    half ^= 1;
+                    l += nb; vr += 8 * nb;
+                }
+            } else if (TMAB > 0 && SCOMP) {
+                // Component signatures through the same ring: per row the chunk of rsurf and, behind it, the chunk of
+                // { C, G, T, Z } quadruples (32 B per evaluation, two STS.128 per column); one thread hands both pieces
+                // of every row to cp.async.bulk.  Whole 128-byte lines leave the SM instead of per-thread 16-byte
+                // pieces of a 32-byte AoS element (the per-thread path reaches 0.46 of the HBM rate).
+                const size_t half_stride = (size_t) TMAB * 5 * chunk;
+                while (l < e) {
+                    const int nb = min(TMAB, e - l);
+                    double* sr = ring + (size_t) half * half_stride + kq;                          // [TMAB][chunk]
+                    double* ss = ring + (size_t) half * half_stride + (size_t) TMAB * chunk;       // [TMAB][chunk][4]
+#pragma unroll
+                    for (int b = 0; b < TMAB; b++) {
+                        if (b < nb) {
+                            const double Kc = vr[8 * b].y, Kt = vr[8 * b + 2].x;
+                            const double2 v3 = vr[8 * b + 3], v6 = vr[8 * b + 6], v7 = vr[8 * b + 7];   // (q,fd) (K'g,K'z) (Kg,Kz)
+#pragma unroll
+                            for (int j = 0; j < LPT; j++) {
+                                const double zg = fma(sG[j], v6.x, sZ[j] * v6.y);             // Z*K'z + G*K'g   gortt.c:514
+                                double Cd = fma(sA[j], v3.x, sPD[j]);                         // CdC + CdCG      gortt.c:504-507
+                                Cd = fma(ke, zg, Cd);                                         // + CdG           gortt.c:528
+                                const double C = fma(v3.y, Cd, sFCf[j]);                      // gortt.c:531
+                                sr[b * chunk + 32 * j] = fma(v7.y, sZ[j], fma(Kt, sT[j], fma(v7.x, sG[j], Kc * C)));   // gortt.c:557
+                                double2* q4 = reinterpret_cast<double2*>(ss + ((size_t) b * chunk + kq + 32 * j) * 4);
+                                q4[0] = make_double2(C, sG[j]);
+                                q4[1] = make_double2(sT[j], sZ[j]);
+                            }
+                        }
+                    }
+                    if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncthreads();
+                    if (tid == 0) {
+                        for (int b = 0; b < nb; b++) {
+                            const size_t go = (size_t) (s0 + l + b) * a.pitch + wbase;
+                            const unsigned sa = (unsigned) __cvta_generic_to_shared(ring + (size_t) half * half_stride + (size_t) b * chunk);
+                            const unsigned sq = (unsigned) __cvta_generic_to_shared(ss + (size_t) b * chunk * 4);
+                            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                                         :: "l"(a.rsurf + go), "r"(sa), "r"(row_bytes) : "memory");
+                            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                                         :: "l"(a.scomp + 4 * go), "r"(sq), "r"(4u * row_bytes) : "memory");
                         }
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }

@@ -582,3 +582,34 @@ def test_forward_batch_equals_the_three_calls(gort):
     with pytest.raises(gort_b200.GortError) as ei:
         gort.forward(small, w["leaf"][:, :7], w["soil"][:, :7], np.array([399.0, 500.0]), shared)
     assert ei.value.code == 3
+
+
+@pytest.mark.parametrize("nw,pitch", [(2101, 2112), (700, 704), (64, 64), (333, 352)])
+def test_component_signatures_through_the_bulk_store_ring(gort, nw, pitch):
+    """-prnspec with 128-byte aligned rows: rsurf and the { C, G, T, Z } quadruples leave through the shared-memory ring
+    and cp.async.bulk; same bits as the per-thread store path (dense host arrays), padding columns hold copies of the
+    last band, columns beyond the padded line are untouched."""
+    import torch
+    rng = np.random.Generator(np.random.PCG64(500 + nw))
+    M, G = 2, 1500
+    st = wk.random_structures(rng, M)
+    leaf = wk.random_leaves(rng, M)
+    wl = np.sort(rng.uniform(400, 2500, nw))
+    sza = np.repeat(rng.uniform(0, 80, G // 30), 30); saa = np.repeat(rng.uniform(0, 360, G // 30), 30)
+    ang = np.stack([rng.uniform(0, 85, G), rng.uniform(0, 360, G), sza, saa])
+    lut = gort.lut(st)
+    rl, tl, rs = gort.spectra(leaf, np.repeat(wk.DEFAULT_SOIL.reshape(4, 1), M, axis=1), wl)
+    r_ref, s_ref = gort.brdf(st, lut, ang, rl, tl, rs, want_scomp=True)          # dense rows: per-thread stores
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    d_r = torch.full((M, G, pitch), -9.0, dtype=torch.float64, device=dev)
+    d_s = torch.full((M, G, pitch, 4), -9.0, dtype=torch.float64, device=dev)
+    gort.brdf_dev(t(st), t(lut), t(ang), t(rl), t(tl), t(rs), d_r, scomp=d_s)
+    gort.synchronize()
+    r, sc = d_r.cpu().numpy(), d_s.cpu().numpy()
+    assert np.array_equal(r[:, :, :nw], r_ref) and np.array_equal(sc[:, :, :nw], s_ref)
+    ncol = min(pitch, (nw + 15) // 16 * 16)
+    if ncol > nw:
+        assert np.array_equal(r[:, :, nw:ncol], np.repeat(r[:, :, nw - 1:nw], ncol - nw, axis=2))
+        assert np.array_equal(sc[:, :, nw:ncol], np.repeat(sc[:, :, nw - 1:nw], ncol - nw, axis=2))
+    assert np.all(r[:, :, ncol:] == -9.0) and np.all(sc[:, :, ncol:] == -9.0)
