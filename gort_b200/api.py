@@ -26,6 +26,7 @@ import numpy as np
 NTH = 91
 LUT_STRIDE = 2 * NTH + 2
 LUT_FULL, LUT_Q08 = 0, 1
+JAC_LAMBDA, JAC_R, JAC_B, JAC_H1, JAC_H2, JAC_FAVD, JAC_LAI = range(7)
 PROSPECT_NW = 2101
 SOIL_TABLE_NW = 2101
 
@@ -59,7 +60,7 @@ ABI_SYMBOLS = [
     "gort_prospect_batch", "gort_brdf_batch", "gort_brdf_batch_dev", "gort_energy_batch",
     "gort_energy_batch_dev", "gort_gauleg", "gort_lut_write_text", "gort_lut_read_text",
     "gort_dfma_peak", "gort_profile_begin", "gort_profile_end", "gort_set_overlap",
-    "gort_forward_batch", "gort_lut_intermediates_batch", "gort_lut_intermediates_batch_dev", "gort_host_alloc_near", "gort_host_alloc_on_cpus", "gort_host_placement", "gort_soil_table_read", "gort_soil_from_table", "gort_soil_from_table_dev",
+    "gort_forward_batch", "gort_jacobian_batch", "gort_lut_intermediates_batch", "gort_lut_intermediates_batch_dev", "gort_host_alloc_near", "gort_host_alloc_on_cpus", "gort_host_placement", "gort_soil_table_read", "gort_soil_from_table", "gort_soil_from_table_dev",
 ]
 
 
@@ -110,6 +111,7 @@ def load_library():
     lib.gort_energy_batch.argtypes = [vp, sp] + [vp] * 9
     lib.gort_energy_batch_dev.argtypes = [vp, vp, sp] + [vp] * 9
     lib.gort_forward_batch.argtypes = [vp, sp, C.c_int, vp, vp, vp, C.c_double, C.c_double, vp, vp, vp, vp]
+    lib.gort_jacobian_batch.argtypes = [vp, sp, C.c_int, C.c_int, C.c_double, vp, vp, vp, C.c_double, C.c_double, vp, vp, vp, vp]
     lib.gort_gauleg.argtypes = [vp, vp, vp]
     lib.gort_lut_write_text.argtypes = [vp, vp]
     lib.gort_lut_write_text.restype = C.c_long
@@ -360,6 +362,25 @@ class Gort:
         self._check(self._lib.gort_forward_batch(self._h, C.byref(sh), method, _ptr(st), _ptr(leaf), _ptr(soil),
                                                  float(user_leaf), float(user_soil), _ptr(wl), _ptr(ang), _ptr(rsurf), _ptr(lut)))
         return (rsurf, lut) if want_lut else rsurf
+
+    def jacobian(self, structure, leaf, soil, wavelength, angles, param=JAC_LAI, rel_step=0.0, method=LUT_FULL,
+                 user_leaf=-1.0, user_soil=-1.0, beta=None, fd=None, want_rsurf=False):
+        """d rsurf / d parameter [M][G][W] by central differences through the whole chain on the GPU
+        (gort_jacobian_batch); param = JAC_LAI (default), JAC_FAVD, JAC_LAMBDA, ... ; optionally rsurf as well."""
+        st = _np(structure)
+        M = st.shape[1]
+        leaf = None if leaf is None else _np(leaf)
+        soil = None if soil is None else _np(soil)
+        wl = _np(wavelength).ravel()
+        ang = _np(angles)
+        G, W = ang.shape[-1], wl.shape[0]
+        sh = self._shape(M, G, W, ang.ndim == 3, 1, beta, fd)
+        jac = np.empty((M, G, W))
+        rsurf = np.empty((M, G, W)) if want_rsurf else None
+        self._check(self._lib.gort_jacobian_batch(self._h, C.byref(sh), method, int(param), float(rel_step), _ptr(st), _ptr(leaf),
+                                                  _ptr(soil), float(user_leaf), float(user_soil), _ptr(wl), _ptr(ang),
+                                                  _ptr(jac), _ptr(rsurf)))
+        return (jac, rsurf) if want_rsurf else jac
 
     def energy(self, structure, lut, angles, rleaf, tleaf, rsoil, beta=None, fd=None):
         st, lut, ang, rl, tl, rs, M, G, W, gps, sps = self._prep(structure, lut, angles, rleaf, tleaf, rsoil)

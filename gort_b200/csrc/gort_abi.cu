@@ -626,6 +626,72 @@ int gort_forward_batch(gort_ctx *ctx, const gort_shape *shape, int lut_method, c
     return check_pipeline_fault(ctx);
 }
 
+// ---- finite-difference Jacobian through the whole chain -----------------------------
+int gort_jacobian_batch(gort_ctx *ctx, const gort_shape *shape, int lut_method, int param, double rel_step,
+                        const double *structure, const double *leaf, const double *soil, double user_leaf,
+                        double user_soil, const double *wavelength, const double *angles, double *jac, double *rsurf)
+{
+    if (!ctx) return GORT_ERR_INVALID;
+    TRY(check_shape(ctx, shape, "gort_jacobian_batch"));
+    if (!structure || !wavelength || !angles || !jac || (user_leaf < 0.0 && !leaf) || (user_soil < 0.0 && !soil))
+        return set_error(ctx, GORT_ERR_INVALID, "gort_jacobian_batch: NULL argument");
+    if (param < GORT_JAC_LAMBDA || param > GORT_JAC_LAI) return set_error(ctx, GORT_ERR_INVALID, "gort_jacobian_batch: unknown parameter %d", param);
+    if (lut_method != GORT_LUT_FULL && lut_method != GORT_LUT_Q08)
+        return set_error(ctx, GORT_ERR_INVALID, "gort_jacobian_batch: unknown LUT method %d", lut_method);
+    const size_t M = shape->n_sets, G = shape->n_geom, W = shape->n_wl;
+    for (size_t i = 0; i < W; i++)
+        if (wavelength[i] < GORT_WL_MIN || wavelength[i] > GORT_WL_MAX)
+            return set_error(ctx, GORT_ERR_RANGE, "wavlength out of range (400-2500)");
+    TRYCUDA(ctx, cudaSetDevice(ctx->device), "cudaSetDevice");
+    const double h = rel_step > 0.0 ? rel_step : 1e-4;
+    const int row = param == GORT_JAC_LAI ? 5 : param;
+    cudaStream_t A = ctx->stream;
+    // members in chunks that keep the three result buffers below ~768 MB
+    size_t C = ((size_t) 256 << 20) / (G * W * sizeof(double));
+    if (C < 1) C = 1;
+    if (C > M) C = M;
+    const bool per_set_geom = shape->geom_per_set != 0;
+    double *d_wl, *d_ang_shared = NULL;
+    TRY(h2d(ctx, 18, wavelength, W, &d_wl));
+    if (!per_set_geom) TRY(h2d(ctx, 19, angles, 4 * G, &d_ang_shared));
+    // slots: 0 structure, 1 leaf, 2 soil, 3 angles, 4 perturbed structure, 5 lut, 6-8 spectra, 9 f+, 10 f-, 11 f0 / jac
+    const size_t sz[12] = {6 * C, 7 * C, 4 * C, per_set_geom ? 4 * C * G : 8, 6 * C, C * GORT_LUT_STRIDE, C * W, C * W, C * W,
+                           C * G * W, C * G * W, C * G * W};
+    double *d[12];
+    for (int k = 0; k < 12; k++) {
+        d[k] = (double *) scratch(ctx, k, sz[k] * sizeof(double));
+        if (!d[k]) return GORT_ERR_NOMEM;
+    }
+    gort_shape sh = *shape;
+    sh.spectra_per_set = 1;
+    sh.out_pitch = 0;
+    for (size_t m0 = 0; m0 < M; m0 += C) {
+        const size_t c = M - m0 < C ? M - m0 : C;
+        sh.n_sets = (int) c;
+        TRY(copy_rows(ctx, A, d[0], c, structure + m0, M, c, 6, cudaMemcpyHostToDevice, "jacobian: structure"));
+        if (user_leaf < 0.0) TRY(copy_rows(ctx, A, d[1], c, leaf + m0, M, c, 7, cudaMemcpyHostToDevice, "jacobian: leaf"));
+        if (user_soil < 0.0) TRY(copy_rows(ctx, A, d[2], c, soil + m0, M, c, 4, cudaMemcpyHostToDevice, "jacobian: soil"));
+        if (per_set_geom) TRY(copy_rows(ctx, A, d[3], c * G, angles + m0 * G, M * G, c * G, 4, cudaMemcpyHostToDevice, "jacobian: angles"));
+        const double *d_ang = per_set_geom ? d[3] : d_ang_shared;
+        TRY(launch_spectra(ctx, A, (int) c, user_leaf < 0.0 ? d[1] : NULL, user_soil < 0.0 ? d[2] : NULL, user_leaf, user_soil,
+                           (int) W, d_wl, d[6], d[7], d[8]));
+        for (int side = 0; side < 2; side++) {
+            TRY(launch_jac_perturb(ctx, A, (int) c, row, side == 0 ? 1.0 + h : 1.0 - h, d[0], d[4]));
+            TRY(launch_lut(ctx, A, (int) c, d[4], lut_method, d[5]));
+            TRY(launch_brdf(ctx, A, sh, d[4], d[5], d_ang, d[6], d[7], d[8], d[9 + side], NULL, NULL));
+        }
+        if (rsurf) {
+            TRY(launch_lut(ctx, A, (int) c, d[0], lut_method, d[5]));
+            TRY(launch_brdf(ctx, A, sh, d[0], d[5], d_ang, d[6], d[7], d[8], d[11], NULL, NULL));
+            TRYCUDA(ctx, cudaMemcpyAsync(rsurf + m0 * G * W, d[11], c * G * W * sizeof(double), cudaMemcpyDeviceToHost, A), "jacobian: rsurf");
+        }
+        TRY(launch_jac_diff(ctx, A, (int) c, (long) (G * W), row, param == GORT_JAC_LAI, h, d[0], d[9], d[10], d[11]));
+        TRYCUDA(ctx, cudaMemcpyAsync(jac + m0 * G * W, d[11], c * G * W * sizeof(double), cudaMemcpyDeviceToHost, A), "jacobian: result");
+    }
+    TRYCUDA(ctx, cudaStreamSynchronize(A), "gort_jacobian_batch");
+    return check_pipeline_fault(ctx);
+}
+
 int gort_energy_batch_dev(gort_ctx *ctx, void *stream, const gort_shape *shape, const double *structure,
                           const double *lut, const double *angles, const double *rleaf, const double *tleaf,
                           const double *rsoil, double *albedo, double *favegt, double *fasoil)

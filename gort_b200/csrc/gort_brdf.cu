@@ -785,6 +785,48 @@ int launch_energy(gort_ctx *ctx, cudaStream_t s, const gort_shape &sh, const dou
 }
 
 // ------------------------------------------------------------------------------------------------
+// Finite-difference Jacobian helpers (gort_jacobian_batch): scale one structure row, form the difference quotient.
+__global__ void __launch_bounds__(256)
+jac_perturb_kernel(int n_sets, int row, double factor, const double* __restrict__ st_in, double* __restrict__ st_out)
+{
+    const long e = (long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= 6L * n_sets) return;
+    const int r = (int) (e / n_sets);
+    st_out[e] = r == row ? st_in[e] * factor : st_in[e];
+}
+
+// jac = (fp - fm) / (2 h p) per member; lai != 0: p = LAI at fixed geometry, (fp - fm) / (2 h LAI) with LAI = favd lambda pi r^2 b 4/3
+__global__ void __launch_bounds__(256)
+jac_diff_kernel(int n_sets, long per_set, int row, int lai, double h, const double* __restrict__ st,
+                const double* __restrict__ fp, const double* __restrict__ fm, double* __restrict__ jac)
+{
+    const long e = (long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= per_set * n_sets) return;
+    const int m = (int) (e / per_set);
+    const size_t N = (size_t) n_sets;
+    double p = st[(size_t) row * N + m];
+    if (lai) p = st[5 * N + m] * (st[0 * N + m] * st[1 * N + m] * st[1 * N + m] * GORT_PI * st[2 * N + m] * 4.0) / 3.0;   // gortt.c:1129 inverted
+    jac[e] = (fp[e] - fm[e]) / (2.0 * h * p);
+}
+
+int launch_jac_perturb(gort_ctx *ctx, cudaStream_t s, int n_sets, int row, double factor, const double *st_in, double *st_out)
+{
+    note_other_work(ctx);
+    jac_perturb_kernel<<<(unsigned) ((6L * n_sets + 255) / 256), 256, 0, s>>>(n_sets, row, factor, st_in, st_out);
+    ctx->launches++;
+    return check_cuda(ctx, cudaGetLastError(), "jac_perturb_kernel launch");
+}
+
+int launch_jac_diff(gort_ctx *ctx, cudaStream_t s, int n_sets, long per_set, int row, int lai, double h, const double *st,
+                    const double *fp, const double *fm, double *jac)
+{
+    note_other_work(ctx);
+    jac_diff_kernel<<<(unsigned) ((per_set * n_sets + 255) / 256), 256, 0, s>>>(n_sets, per_set, row, lai, h, st, fp, fm, jac);
+    ctx->launches++;
+    return check_cuda(ctx, cudaGetLastError(), "jac_diff_kernel launch");
+}
+
+// ------------------------------------------------------------------------------------------------
 // gauleg, gortt_albedo.c:141-199, n = 32 on (-1, 1).  One thread per root.
 __global__ void gauleg_kernel(double* __restrict__ out)
 {

@@ -89,6 +89,9 @@ int launch_spectra(gort_ctx *ctx, cudaStream_t s, int n_sets, const double *leaf
                    double *rleaf, double *tleaf, double *rsoil);
 int launch_soil_table(gort_ctx *ctx, cudaStream_t s, const double *table, int n_sets, int n_wl, const double *wl, double *rsoil);
 int launch_prospect_full(gort_ctx *ctx, cudaStream_t s, int n_sets, const double *leaf, double *refl, double *tran);
+int launch_jac_perturb(gort_ctx *ctx, cudaStream_t s, int n_sets, int row, double factor, const double *st_in, double *st_out);
+int launch_jac_diff(gort_ctx *ctx, cudaStream_t s, int n_sets, long per_set, int row, int lai, double h, const double *st,
+                    const double *fp, const double *fm, double *jac);
 int launch_gauleg(gort_ctx *ctx, cudaStream_t s, double *d_out /*[2][32]*/);
 int launch_tav_tables(gort_ctx *ctx, cudaStream_t s, double *d_prospect);
 int upload_soil_tables(gort_ctx *ctx, cudaStream_t s, double *d_soil);

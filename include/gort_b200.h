@@ -199,6 +199,24 @@ int gort_forward_batch(gort_ctx *ctx, const gort_shape *shape, int lut_method, c
                        const double *leaf, const double *soil, double user_leaf, double user_soil,
                        const double *wavelength, const double *angles, double *rsurf, double *lut_out);
 
+/* ---- Jacobian of the BRDF with respect to one canopy parameter (for variational data
+ *      assimilation; the reference has no derivative code -- its only hook is the LAI -> favd mapping of
+ *      gortt.c:1127-1131, favd = 3 LAI / (4 lambda pi r^2 b)).
+ *      Central differences through the whole chain on the GPU: for every member the chosen structure row is scaled by
+ *      (1 +- rel_step), gap probabilities and BRDF are evaluated for both (the spectra once), and a difference kernel
+ *      forms  d rsurf / d p = (f(p (1 + h)) - f(p (1 - h))) / (2 h p);  only the Jacobian (and, if asked for, the
+ *      unperturbed rsurf) travels back.  Host pointers; arguments as gort_forward_batch.
+ *      param: GORT_JAC_LAMBDA .. GORT_JAC_FAVD = the structure row itself; GORT_JAC_LAI = leaf area index at fixed crown
+ *      geometry, i.e. d/d favd times favd / LAI.  rel_step <= 0 selects 1e-4 (truncation ~1e-8 relative, rounding
+ *      ~1e-12 / h).  The chain is smooth in lambda and favd (LAI); in r, b, h1, h2 it is only piecewise smooth -- the
+ *      path-length histogram of gortt_get_pd_s bins on the crown shape ((int)(s/ds + 0.5), gortt_pn_kopen.c:134-139) --
+ *      so those derivatives carry jumps of the size of a bin flip divided by the step.
+ *      jac [M][G][W]; rsurf (optional, may be NULL) [M][G][W]. */
+enum { GORT_JAC_LAMBDA = 0, GORT_JAC_R = 1, GORT_JAC_B = 2, GORT_JAC_H1 = 3, GORT_JAC_H2 = 4, GORT_JAC_FAVD = 5, GORT_JAC_LAI = 6 };
+int gort_jacobian_batch(gort_ctx *ctx, const gort_shape *shape, int lut_method, int param, double rel_step,
+                        const double *structure, const double *leaf, const double *soil, double user_leaf,
+                        double user_soil, const double *wavelength, const double *angles, double *jac, double *rsurf);
+
 /* ---- energy balance: replaces gortt_energy / gortt_albedo / gauleg (include/gortt.h:273-275;
  *      gortt.c:208-209, :322).  One result per input line (only sza/saa of the line matter):
  *      albedo, favegt, fasoil are [M][G][W]. ---------------------------------------------- */
