@@ -105,6 +105,7 @@ int gort_create(int device, gort_ctx **out)
     ctx->dbg_no_pdl = getenv("GORT_NO_PDL") ? 1 : 0;
     ctx->dbg_no_tma = getenv("GORT_NO_TMA") ? 1 : 0;
     ctx->dbg_rows_on = getenv("GORT_ROWS") ? 1 : 0;
+    ctx->dbg_table_on = getenv("GORT_WIDE_TABLE") ? 1 : 0;
     ctx->dbg_rows = getenv("GORT_ROWS_DBG") ? atoi(getenv("GORT_ROWS_DBG")) : 0;
     ctx->dbg_timeline = getenv("GORT_TIMELINE") ? atoi(getenv("GORT_TIMELINE")) : 0;
     if (rc == GORT_OK) rc = launch_gauleg(ctx, ctx->stream, ctx->d_gauleg);
@@ -496,6 +497,9 @@ int gort_brdf_batch_dev(gort_ctx *ctx, void *stream, const gort_shape *shape, co
     return launch_brdf(ctx, pick(ctx, stream), *shape, structure, lut, angles, rleaf, tleaf, rsoil, rsurf, scomp, kprop);
 }
 
+static int copy_rows(gort_ctx *ctx, cudaStream_t s, double *dst, size_t dst_pitch, const double *src, size_t src_pitch,
+                     size_t width, int rows, cudaMemcpyKind kind, const char *what);
+
 struct Staged { double *st, *lut, *ang, *rl, *tl, *rs; };
 
 static int stage_inputs(gort_ctx *ctx, const gort_shape *sh, const double *structure, const double *lut,
@@ -525,9 +529,8 @@ int gort_brdf_batch(gort_ctx *ctx, const gort_shape *shape, const double *struct
     Staged d;
     TRY(stage_inputs(ctx, shape, structure, lut, angles, rleaf, tleaf, rsoil, &d));
     size_t nl = (size_t) shape->n_sets * shape->n_geom;
-    // the device buffer uses the caller's row pitch so that the result comes back in ONE contiguous copy
-    // (a pitched 2-D copy costs more over PCIe than aligned rows save in the kernel); padding columns of a
-    // pitched host array are left undefined
+    // the device buffer uses the caller's row pitch: a dense host array comes back in ONE contiguous copy, a pitched
+    // one row by row (2-D copy) so that its padding columns stay untouched
     const size_t W = shape->n_wl;
     const size_t hp = shape->out_pitch > 0 ? (size_t) shape->out_pitch : W;
     if (hp < W) return set_error(ctx, GORT_ERR_INVALID, "gort_brdf_batch: out_pitch smaller than n_wl");
@@ -536,8 +539,15 @@ int gort_brdf_batch(gort_ctx *ctx, const gort_shape *shape, const double *struct
     TRY(dout(ctx, 7, scomp, 4 * nl * hp, &d_scomp));
     TRY(dout(ctx, 8, kprop, 4 * nl, &d_kprop));
     TRY(launch_brdf(ctx, ctx->stream, *shape, d.st, d.lut, d.ang, d.rl, d.tl, d.rs, d_rsurf, d_scomp, d_kprop));
-    TRY(d2h(ctx, rsurf, d_rsurf, nl * hp));
-    TRY(d2h(ctx, scomp, d_scomp, 4 * nl * hp));
+    if (hp == W) {
+        TRY(d2h(ctx, rsurf, d_rsurf, nl * hp));
+        TRY(d2h(ctx, scomp, d_scomp, 4 * nl * hp));
+    } else {
+        // pitched host rows: only the n_wl columns of every row are copied back -- the padding columns of the caller's
+        // array are never touched, as the header promises (the device buffer's padding holds kernel scratch)
+        TRY(copy_rows(ctx, ctx->stream, rsurf, hp, d_rsurf, hp, W, (int) nl, cudaMemcpyDeviceToHost, "device to host copy"));
+        if (scomp) TRY(copy_rows(ctx, ctx->stream, scomp, 4 * hp, d_scomp, 4 * hp, 4 * W, (int) nl, cudaMemcpyDeviceToHost, "device to host copy"));
+    }
     TRY(d2h(ctx, kprop, d_kprop, 4 * nl));
     TRY(check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "gort_brdf_batch"));
     return check_pipeline_fault(ctx);

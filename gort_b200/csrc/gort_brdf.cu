@@ -255,9 +255,20 @@ struct BrdfPlan {
     unsigned long long *flags;      // this call's flag array: geometry tiles, then table tiles
     bool pdl;                       // launch as a programmatic dependent of the geometry kernel
     bool gate;                      // overlap mode: wait per CTA for the previous launch's CTA of the same index
+    const double *table;            // per-call (set, lambda) table for the wide kernel's TMA variants, or NULL
+    int tab_ncol;
+    long tab_flag_base;
 };
 
-template <int LPT, bool SCOMP, int MINB, int TMAB>
+// chunking of the wide kernel for a given variant: as few wavelength chunks as possible with <= pick threads per CTA
+static void wide_chunking(int n_col, int lpt, int pick, int *n_chunks, int *threads)
+{
+    *n_chunks = (n_col + lpt * pick - 1) / (lpt * pick);
+    int t = (n_col + *n_chunks * lpt - 1) / (*n_chunks * lpt);
+    *threads = ((t + 31) / 32) * 32;
+}
+
+template <int LPT, bool SCOMP, int MINB, int TMAB, bool TAB = false>
 static int launch_wide(gort_ctx *ctx, cudaStream_t s, const gort_shape &sh, const BrdfPlan &pl, const double *structure,
                        const double *lut, const double *rleaf, const double *tleaf,
                        const double *rsoil, double *rsurf, double *scomp)
@@ -270,10 +281,10 @@ static int launch_wide(gort_ctx *ctx, cudaStream_t s, const gort_shape &sh, cons
     // wavelength chunks: as few as possible with <= WIDE_PICK_THREADS threads per CTA, lanes spread evenly
     // block size cap: with the TMA row ring two CTAs must still fit an SM's shared memory
     const int pick = TMAB > 0 ? WIDE_PICK_THREADS_TMA : WIDE_PICK_THREADS;
-    const int n_chunks = (n_col + LPT * pick - 1) / (LPT * pick);
-    int threads = (n_col + n_chunks * LPT - 1) / (n_chunks * LPT);
-    threads = ((threads + 31) / 32) * 32;
+    int n_chunks, threads;
+    wide_chunking(n_col, LPT, pick, &n_chunks, &threads);
     WideArgs a;
+    a.table = TAB ? pl.table : NULL; a.tab_ncol = pl.tab_ncol; a.tab_flag_base = pl.tab_flag_base;
     a.n_sets = sh.n_sets; a.n_geom = sh.n_geom; a.n_wl = sh.n_wl; a.spectra_per_set = sh.spectra_per_set;
     a.chunk = LPT * threads;
     a.n_col = n_col;
@@ -287,12 +298,12 @@ static int launch_wide(gort_ctx *ctx, cudaStream_t s, const gort_shape &sh, cons
     constexpr int RINGW = SCOMP ? 5 : 1;                  // doubles per evaluation in the output ring
     const size_t smem = sizeof(double2) * 8 * STAGE + sizeof(unsigned) * 4
                       + sizeof(double) * (WIDE_NLEAF + 2 * TMAB * RINGW) * (size_t) a.chunk;
-    auto kern = rsurf_wide_kernel<LPT, SCOMP, MINB, TMAB>;
+    auto kern = rsurf_wide_kernel<LPT, SCOMP, MINB, TMAB, TAB>;
     // occupancy of this (variant, block size) is looked up once per context
     int occ = 0;
     for (int i = 0; i < ctx->n_wide_plan; i++) {
         auto &wp = ctx->wide_plan[i];
-        if (wp.key_lpt == LPT && wp.key_scomp == (int) SCOMP + 2 * TMAB && wp.key_minb == MINB && wp.key_threads == threads) occ = wp.occ;
+        if (wp.key_lpt == LPT && wp.key_scomp == (int) SCOMP + 2 * TMAB + 16 * (int) TAB && wp.key_minb == MINB && wp.key_threads == threads) occ = wp.occ;
     }
     if (occ == 0) {
         // allow the largest chunk any block size can ask for, so that the attribute never shrinks
@@ -304,7 +315,7 @@ static int launch_wide(gort_ctx *ctx, cudaStream_t s, const gort_shape &sh, cons
         if (e != cudaSuccess || occ < 1) occ = 1;
         if (ctx->n_wide_plan < 8) {
             auto &wp = ctx->wide_plan[ctx->n_wide_plan++];
-            wp.key_lpt = LPT; wp.key_scomp = (int) SCOMP + 2 * TMAB; wp.key_minb = MINB; wp.key_threads = threads; wp.key_wl = sh.n_wl; wp.occ = occ;
+            wp.key_lpt = LPT; wp.key_scomp = (int) SCOMP + 2 * TMAB + 16 * (int) TAB; wp.key_minb = MINB; wp.key_threads = threads; wp.key_wl = sh.n_wl; wp.occ = occ;
         }
     }
     // one resident wave: grid.y contiguous line ranges so that n_chunks * grid.y ~ SMs * occupancy
@@ -448,7 +459,21 @@ int launch_brdf(gort_ctx *ctx, cudaStream_t s, const gort_shape &sh, const doubl
     const int bi = ctx->rec_idx;
     const RowsShape rs = sh.n_wl >= 64 ? rows_shape(ctx, sh, L, rsurf, scomp) : RowsShape{};
     const size_t geom_tiles = (size_t) ((L + 31) / 32);
-    const size_t tab_tiles = rs.ok ? (size_t) sh.n_sets * rs.tiles_per_set : 0;
+    // EXPERIMENTAL, off unless GORT_WIDE_TABLE=1: the wide kernel's TMA variants can take their (set, lambda) table from the
+    // geometry kernel's spare CTAs instead of computing it per CTA.  Measured on C2: 45.1 us per launch against 43.8 us,
+    // 41.1 us per overlapped step against 36.6 us -- the per-CTA computation runs under the previous CTA's stores for free,
+    // the table copy competes with them for L2
+    int wt_ncol = 0;
+    if (ctx->dbg_table_on && !rs.ok && sh.n_wl >= 64 && !ctx->dbg_no_tma && pitch % 16 == 0 && ((size_t) rsurf & 15) == 0 && ((size_t) scomp & 15) == 0) {
+        const long padded = (long) (sh.n_wl + 15) / 16 * 16;
+        const int n_col = (int) (padded < pitch ? padded : pitch);
+        int nc, thr;
+        wide_chunking(n_col, scomp ? 2 : 4, WIDE_PICK_THREADS_TMA, &nc, &thr);
+        const int chunk = (scomp ? 2 : 4) * thr;
+        if (chunk % 128 == 0 && (size_t) sh.n_sets * WIDE_NLEAF * nc * chunk * sizeof(double) <= ((size_t) 256 << 20)) wt_ncol = nc * chunk;
+    }
+    const int tab_ncol = rs.ok ? rs.ncolt : wt_ncol;
+    const size_t tab_tiles = tab_ncol ? (size_t) sh.n_sets * (tab_ncol / ROWS_TAB_TILE) : 0;
     {
         int rc = ensure_flags(ctx, s, bi, geom_tiles + tab_tiles);
         if (rc != GORT_OK) return rc;
@@ -456,8 +481,8 @@ int launch_brdf(gort_ctx *ctx, cudaStream_t s, const gort_shape &sh, const doubl
     double *rec = (double *) rec_buffer(ctx, bi, sizeof(double) * GORT_REC_STRIDE * (size_t) L);
     if (!rec) return GORT_ERR_NOMEM;
     double *table = NULL;
-    if (rs.ok) {
-        table = (double *) tab_buffer(ctx, bi, sizeof(double) * rs.tab_doubles);
+    if (tab_ncol) {
+        table = (double *) tab_buffer(ctx, bi, sizeof(double) * (size_t) sh.n_sets * ROWS_NLEAF * tab_ncol);
         if (!table) return GORT_ERR_NOMEM;
     }
     cudaEvent_t *ev = (ctx->prof_ev && ctx->prof_n < ctx->prof_cap) ? ctx->prof_ev + 3 * ctx->prof_n : NULL;
@@ -492,8 +517,8 @@ int launch_brdf(gort_ctx *ctx, cudaStream_t s, const gort_shape &sh, const doubl
             ctx->geom_carveout_set = 1;
         }
         TableJob tj = {};
-        if (rs.ok) {
-            tj.n_tiles = (int) tab_tiles; tj.n_wl = sh.n_wl; tj.spectra_per_set = sh.spectra_per_set; tj.ncolt = rs.ncolt;
+        if (tab_ncol) {
+            tj.n_tiles = (int) tab_tiles; tj.n_wl = sh.n_wl; tj.spectra_per_set = sh.spectra_per_set; tj.ncolt = tab_ncol;
             tj.rleaf = rleaf; tj.tleaf = tleaf; tj.rsoil = rsoil; tj.table = table;
             tj.flags = ctx->d_flags[bi] + geom_tiles;
         }
@@ -529,6 +554,7 @@ int launch_brdf(gort_ctx *ctx, cudaStream_t s, const gort_shape &sh, const doubl
         pl.L = L; pl.rec = rec; pl.flags = ctx->d_flags[bi];
         pl.pdl = use_pdl && !ev;
         pl.gate = early_geom;
+        pl.table = rs.ok ? NULL : table; pl.tab_ncol = tab_ncol; pl.tab_flag_base = (long) geom_tiles;
         int rc;
         if (rs.ok) {
             // full spectrum, aligned rows: one persistent CTA per SM writes whole rows (gort_rsurf_rows.cuh)
@@ -552,8 +578,11 @@ int launch_brdf(gort_ctx *ctx, cudaStream_t s, const gort_shape &sh, const doubl
             // Output path: rows through shared memory and TMA bulk stores (3 rows per CTA barrier, LPT = 4) when the
             // rows are 128-byte aligned, else per-thread stores
             const bool tma = !ctx->dbg_no_tma && pitch % 16 == 0 && ((size_t) rsurf & 15) == 0 && ((size_t) scomp & 15) == 0;
-            if (scomp && tma) rc = launch_wide<2, true, 2, WIDE_TMA_ROWS_SCOMP>(WIDE_ARGS);
+            const bool tab = pl.table != NULL;
+            if (scomp && tma && tab) rc = launch_wide<2, true, 2, WIDE_TMA_ROWS_SCOMP, true>(WIDE_ARGS);
+            else if (scomp && tma) rc = launch_wide<2, true, 2, WIDE_TMA_ROWS_SCOMP>(WIDE_ARGS);
             else if (scomp) rc = launch_wide<2, true, 2, 0>(WIDE_ARGS);
+            else if (tma && tab) rc = launch_wide<4, false, 2, WIDE_TMA_ROWS, true>(WIDE_ARGS);
             else if (tma) rc = launch_wide<4, false, 2, WIDE_TMA_ROWS>(WIDE_ARGS);
             else if (lpt == 4) rc = launch_wide<4, false, 2, 0>(WIDE_ARGS);
             else if (lpt == 3) rc = launch_wide<3, false, 2, 0>(WIDE_ARGS);

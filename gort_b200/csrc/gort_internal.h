@@ -49,8 +49,8 @@ struct gort_ctx {
     int n_wide_plan;
     int geom_carveout_set, rows_attr_set, lut_attr_set;
     // development switches, read once from the environment by gort_create (A/B measurements in DESIGN.md):
-    // GORT_NO_PDL, GORT_NO_TMA, GORT_ROWS (experimental full-spectrum kernel), GORT_ROWS_DBG, GORT_TIMELINE=<call number>
-    int dbg_no_pdl, dbg_no_tma, dbg_rows_on, dbg_timeline, dbg_rows;
+    // GORT_NO_PDL, GORT_NO_TMA, GORT_WIDE_TABLE (experimental per-call table in the chunked kernel), GORT_ROWS (experimental full-spectrum kernel), GORT_ROWS_DBG, GORT_TIMELINE=<call number>
+    int dbg_no_pdl, dbg_no_tma, dbg_rows_on, dbg_timeline, dbg_rows, dbg_table_on;
     unsigned long long *d_timeline;
     int timeline_calls;
     // pinned-buffer placement (gort_host_alloc_near): probed once

@@ -200,6 +200,21 @@ __device__ __noinline__ double cylind(double r, double h1, double h2, double h)
     return volume;
 }
 
+// gortt_cylind (gortt_pn_kopen.c:891-924) called with h2 == r, as both call sites that are live for h = 0 do (:702,
+// :743).  Then, with the unfused arithmetic this file is compiled with, r*r - h2*h2 is exactly 0 (App. B1), so
+// tmp2 = 0, cylind_fcn(h2, r) = 0 + .5 r^2 asin(1) and the h2 < r tail is skipped: two square roots, one asin and one
+// division fewer than the general routine, same value.
+__device__ __forceinline__ double cylind_to_r(double r, double h1, double h)
+{
+    double slope = h / (r - h1);
+    double tmp1 = sqrt(r * r - h1 * h1);
+    double volume = tmp1 * tmp1 * tmp1 - 0.0;
+    volume /= 3.0;
+    volume -= h1 * ((.50 * r * 0.0 + .50 * r * r * asin(1.0)) - cylind_fcn(h1, r));
+    volume *= 2.0 * slope;
+    return volume;
+}
+
 // gortt_pn_kopen.c:665-768; hp_h = height_p[h], hp_s = height_p[h_s]
 __device__ __noinline__ double tube_vol(const Crown& c, const Ang& a, double hp_h, double hp_s, double h_b)
 {
@@ -239,7 +254,7 @@ __device__ __noinline__ double tube_vol(const Crown& c, const Ang& a, double hp_
         h_tt = (hp_s + r * a.s - h_b) / a.c;
         double hh1 = (h_b - hp_s) / a.s;
         double tmp_h = (hp_s - hp_h) / a.c;
-        V_cyln = GORT_PI * r * r * tmp_h - cylind(r, hh1, r, h_tt);
+        V_cyln = GORT_PI * r * r * tmp_h - cylind_to_r(r, hh1, h_tt);
         V_sp2 = trisec(h_b, hp_s, a, r);
         V_sp1 = (2.0 / 3.0) * GORT_PI * c.rrr;
         V = V_cyln + V_sp2 + V_sp1;
@@ -360,7 +375,10 @@ struct LutWork {
     double *vg;         // [n][15][LUT_ZW]   v_g[h][t]
     double *tube;       // [n][13][LUT_ZW]   tube-volume difference per entry height
     double *es_all;     // [n][15][LUT_ZW]   E[S] towards every layer (only the intermediates path, launch_lut_dead)
+    double *shp;        // [n][LUT_SHP]      derived crown-shape scalars and the 15 layer heights (seven FP64 divisions per
+                        //                   set, done once by lut_plan_kernel instead of by every thread of every kernel)
 };
+#define LUT_SHP 32
 
 __device__ __forceinline__ bool same_shape(const double* __restrict__ st, size_t n, int a, int b)
 {
@@ -368,9 +386,9 @@ __device__ __forceinline__ bool same_shape(const double* __restrict__ st, size_t
            st[3 * n + a] == st[3 * n + b] && st[4 * n + a] == st[4 * n + b];
 }
 
-// Crown shape of set m: gortt_init_params, gortt.c:641-697 (the shape-only part)
+// Crown shape of set m: gortt_init_params, gortt.c:641-697 (the shape-only part) and the layer heights of :778-781
 struct Shape { Crown c; double ellip, h1, h2, z2, dz; };
-__device__ __forceinline__ Shape shape_load(const double* __restrict__ structure, size_t N, int m)
+__device__ __forceinline__ Shape shape_compute(const double* __restrict__ structure, size_t N, int m)
 {
     Shape S;
     const double r = structure[1 * N + m], b = structure[2 * N + m];
@@ -388,10 +406,30 @@ __device__ __forceinline__ Shape shape_load(const double* __restrict__ structure
     S.c.lv_p = 0.0; S.c.tau_p = 0.0;
     return S;
 }
-// height_p[i], gortt.c:778-781
-__device__ __forceinline__ double layer_height_p(const Shape& S, int i)
+// slots of the per-set shape table
+enum { SHP_ELLIP = 0, SHP_R, SHP_H1, SHP_H2, SHP_Z2, SHP_DZ, SHP_Z2P, SHP_H1P, SHP_H2P, SHP_DZP, SHP_HP = 16 };
+__device__ __forceinline__ void shape_store(double* __restrict__ o, const Shape& S)
 {
-    return (S.z2 - S.dz * (double) (GORT_NLAYERS - 1 - i)) / S.ellip;
+    o[SHP_ELLIP] = S.ellip; o[SHP_R] = S.c.r; o[SHP_H1] = S.h1; o[SHP_H2] = S.h2; o[SHP_Z2] = S.z2; o[SHP_DZ] = S.dz;
+    o[SHP_Z2P] = S.c.z2_p; o[SHP_H1P] = S.c.h1_p; o[SHP_H2P] = S.c.h2_p; o[SHP_DZP] = S.c.dz_p;
+    for (int i = 0; i < GORT_NLAYERS; i++) o[SHP_HP + i] = (S.z2 - S.dz * (double) (GORT_NLAYERS - 1 - i)) / S.ellip;   // height_p[i], gortt.c:778-781
+}
+__device__ __forceinline__ Shape shape_load(const LutWork& w, int i)
+{
+    const double* __restrict__ o = w.shp + (size_t) i * LUT_SHP;
+    Shape S;
+    S.ellip = o[SHP_ELLIP]; S.h1 = o[SHP_H1]; S.h2 = o[SHP_H2]; S.z2 = o[SHP_Z2]; S.dz = o[SHP_DZ];
+    const double r = o[SHP_R];
+    S.c.r = r; S.c.rr = r * r; S.c.rrr = S.c.rr * r;
+    S.c.z2_p = o[SHP_Z2P]; S.c.h1_p = o[SHP_H1P]; S.c.h2_p = o[SHP_H2P];
+    S.c.ds = S.dz; S.c.dz_p = o[SHP_DZP];
+    S.c.lv_p = 0.0; S.c.tau_p = 0.0;
+    return S;
+}
+// height_p[i] of set i's shape
+__device__ __forceinline__ double layer_height_p(const LutWork& w, int i, int layer)
+{
+    return w.shp[(size_t) i * LUT_SHP + SHP_HP + layer];
 }
 
 // Groups and sub-groups.  m0 + i is the global index of set i of this pass: group boundaries sit at multiples of
@@ -417,6 +455,7 @@ lut_plan_kernel(int n, int m0, int group_cap, const double* __restrict__ structu
                same_shape(structure, N, m0 + i + nj, m0 + i + nj - 1) && structure[0 * N + m0 + i + nj] == lambda) nj++;
     }
     w.sub[i] = nj;
+    shape_store(w.shp + (size_t) i * LUT_SHP, shape_compute(structure, N, m));
 }
 
 // theta' and its trig, E[S]: one thread per (group head, zenith)
@@ -426,7 +465,7 @@ lut_prep_kernel(int n, int m0, const double* __restrict__ structure, size_t N, L
     const long e = (long) blockIdx.x * blockDim.x + threadIdx.x;
     const int i = (int) (e / LUT_ZW), t = (int) (e - (long) i * LUT_ZW);
     if (i >= n || w.head[i] != i || t >= GORT_NTH) return;
-    const Shape S = shape_load(structure, N, m0 + i);
+    const Shape S = shape_load(w, i);
     const double dth = 1 * GORT_PI / 180.0;
     double theta = dth * (double) t;                                             // gortt.c:783-797
     if (theta >= GORT_PI / 2.0) theta = GORT_PI / 2.0 - 1.0 * GORT_PI / 180.0;
@@ -436,7 +475,7 @@ lut_prep_kernel(int n, int m0, const double* __restrict__ structure, size_t N, L
     a.th = th; a.s = sin(th); a.c = cos(th); a.t = tan(th);
     double* o = w.trig + (size_t) i * 4 * LUT_ZW + t;
     o[0 * LUT_ZW] = a.s; o[1 * LUT_ZW] = a.c; o[2 * LUT_ZW] = a.t;
-    o[3 * LUT_ZW] = t < GORT_NTH - 1 ? expected_single_crown_path(S.c, a, layer_height_p(S, 0)) : 0.0;   // :445
+    o[3 * LUT_ZW] = t < GORT_NTH - 1 ? expected_single_crown_path(S.c, a, layer_height_p(w, i, 0)) : 0.0;   // :445
 }
 
 __device__ __forceinline__ Ang ang_load(const LutWork& w, int i, int t)
@@ -461,7 +500,7 @@ lut_vg_kernel(int n, int m0, const double* __restrict__ structure, size_t N, Lut
     const long e = (long) blockIdx.x * blockDim.x + threadIdx.x;
     const int i = (int) (e / LUT_ZW), t = (int) (e - (long) i * LUT_ZW);
     if (i >= n || w.head[i] != i || t >= GORT_NTH) return;
-    const Shape S = shape_load(structure, N, m0 + i);
+    const Shape S = shape_load(w, i);
     const Ang a = ang_load(w, i, t);
     double* vg = w.vg + (size_t) i * GORT_NLAYERS * LUT_ZW + t;
     // crown-centre heights of the midpoint rule, gortt_pn_kopen.c:162: a running sum
@@ -477,7 +516,7 @@ lut_vg_kernel(int n, int m0, const double* __restrict__ structure, size_t N, Lut
     }
     if (K < 1 || K >= 16) {
 #pragma unroll 1
-        for (int h = 0; h < GORT_NLAYERS; h++) vg[(size_t) h * LUT_ZW] = proj_volume(S.c, a, layer_height_p(S, h));
+        for (int h = 0; h < GORT_NLAYERS; h++) vg[(size_t) h * LUT_ZW] = proj_volume(S.c, a, layer_height_p(w, i, h));
         return;
     }
     // distinct cross-sections j = 0 .. 13 + K: (h, z) = (0, K-1-j) for j < K, (j-K+1, 0) after
@@ -487,7 +526,7 @@ lut_vg_kernel(int n, int m0, const double* __restrict__ structure, size_t N, Lut
         const int ih = max(0, j - (K - 1)), k = ih - (j - (K - 1));
 #pragma unroll
         for (int q = 0; q < 16; q++) if (q == k) zsel = zk[q];
-        s_A[j][threadIdx.x] = cross_section(S.c, a, layer_height_p(S, ih), zsel);
+        s_A[j][threadIdx.x] = cross_section(S.c, a, layer_height_p(w, i, ih), zsel);
     }
 #pragma unroll 1
     for (int h = 0; h < GORT_NLAYERS; h++) {
@@ -506,10 +545,10 @@ lut_tube_kernel(int n, int m0, const double* __restrict__ structure, size_t N, L
     const int lane = threadIdx.x & 31, k = threadIdx.x >> 5;
     const int t = blockIdx.y * 32 + lane;
     if (t >= GORT_NTH - 1) return;                                               // epgap only for t < nth - 1, :1099
-    const Shape S = shape_load(structure, N, m0 + i);
+    const Shape S = shape_load(w, i);
     const Ang a = ang_load(w, i, t);
-    const double hp0 = layer_height_p(S, 0);
-    const double hps = layer_height_p(S, GORT_NLAYERS - 2 - k);                  // :457, sp_i = 13 down to 1
+    const double hp0 = layer_height_p(w, i, 0);
+    const double hps = layer_height_p(w, i, GORT_NLAYERS - 2 - k);                  // :457, sp_i = 13 down to 1
     w.tube[((size_t) i * LUT_NSP + k) * LUT_ZW + t] = tube_vol(S.c, a, hp0, hps, S.c.h2_p) - tube_vol(S.c, a, hp0, hps, S.c.h1_p);
 }
 
@@ -536,7 +575,7 @@ lut_crown_kernel(int n, int m0, const double* __restrict__ structure, size_t N, 
     const int lane = threadIdx.x & 31, k = threadIdx.x >> 5;
     const int t = blockIdx.y * 32 + lane;
     const int m = m0 + i;
-    const Shape S = shape_load(structure, N, m);
+    const Shape S = shape_load(w, i);
     const double lambda = structure[0 * N + m];
     const double lv = lambda / (S.h2 - S.h1);
     const double lv_p = lv * S.ellip;
@@ -565,8 +604,8 @@ lut_crown_kernel(int n, int m0, const double* __restrict__ structure, size_t N, 
         const double P_s_p = exp(-1.0 * lv_p * vg[(size_t) (sp_i + 1) * LUT_ZW]) - exp(-1.0 * lv_p * vg[(size_t) sp_i * LUT_ZW]);   // :43, :482
         const double temp1 = w.tube[((size_t) hd * LUT_NSP + k) * LUT_ZW + t] * lv_p;   // :497
         const double E = exp(-temp1);
-        const double hp0 = layer_height_p(S, 0);
-        const double sp = (double) (layer_height_p(S, sp_i) - hp0) / a_c;       // :464
+        const double hp0 = layer_height_p(w, i, 0);
+        const double sp = (double) (layer_height_p(w, i, sp_i) - hp0) / a_c;       // :464
         // crown-count loop, gortt_pn_kopen.c:489-527, with its loop invariants hoisted:
         //   P(n) P(s') = temp1^n e^-temp1 / (n! (1 - e^-temp1)) P(s')        :501-502, :522
         //   s          = s' (1 - exp(-n E[S]/s'))                            :508
@@ -653,9 +692,9 @@ lut_es_all_kernel(int n, int m0, const double* __restrict__ structure, size_t N,
     const int z = (int) ((e / LUT_ZW) % GORT_NLAYERS);
     const int i = (int) (e / ((long) LUT_ZW * GORT_NLAYERS));
     if (i >= n || w.head[i] != i || t >= GORT_NTH) return;
-    const Shape S = shape_load(structure, N, m0 + i);
+    const Shape S = shape_load(w, i);
     const Ang a = ang_load(w, i, t);
-    w.es_all[((size_t) i * GORT_NLAYERS + z) * LUT_ZW + t] = expected_single_crown_path(S.c, a, layer_height_p(S, z));   // gortt_get_es(p, z, t)
+    w.es_all[((size_t) i * GORT_NLAYERS + z) * LUT_ZW + t] = expected_single_crown_path(S.c, a, layer_height_p(w, i, z));   // gortt_get_es(p, z, t)
 }
 
 struct DeadOut { double *vb, *fb, *t_open, *dt_open, *dk_open, *k_open; };
@@ -669,7 +708,7 @@ lut_dead_kernel(int n, int m0, const double* __restrict__ structure, size_t N, L
     __shared__ double s_f1[GORT_NLAYERS][LUT_ZW];          // p_n0[h][t] sin(2 theta_t)
     const int i = blockIdx.x, m = m0 + i, hd = w.head[i];
     const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
-    const Shape S = shape_load(structure, N, m);
+    const Shape S = shape_load(w, i);
     const double lambda = structure[0 * N + m], favd = structure[5 * N + m];
     const double lv_p = (lambda / (S.h2 - S.h1)) * S.ellip;                       // gortt.c:671, :677
     const double tau_p = 0.5 * (favd * S.ellip);                                  // :675-676
@@ -677,7 +716,7 @@ lut_dead_kernel(int n, int m0, const double* __restrict__ structure, size_t N, L
     const double r = S.c.r;
     if (threadIdx.x < GORT_NLAYERS) {
         // gortt_calc_vb, :938-970: sphere centred at layer height, cut by the h1 and h2 planes
-        const double hp = layer_height_p(S, threadIdx.x);
+        const double hp = layer_height_p(w, i, threadIdx.x);
         double Vol = 4.0 * GORT_PI * S.c.rrr / 3.0, tmp;
         if (hp + r > S.c.h2_p) { tmp = hp + r - S.c.h2_p; Vol -= GORT_PI * tmp * tmp * (3.0 * r - tmp) / 3.0; }
         if (hp - r < S.c.h1_p) { tmp = S.c.h1_p - (hp - r); Vol -= GORT_PI * tmp * tmp * (3.0 * r - tmp) / 3.0; }
@@ -861,7 +900,7 @@ int launch_lut_dead(gort_ctx *ctx, cudaStream_t s, int n_sets, const double *str
     if (cap < 1) cap = 1;
     if (cap > LUT_GROUP_CAP) cap = LUT_GROUP_CAP;
     const int chunk = n_sets < LUT_CHUNK / 2 ? n_sets : LUT_CHUNK / 2;
-    const size_t per_set = sizeof(double) * (4 + 2 * GORT_NLAYERS + LUT_NSP) * LUT_ZW + 2 * sizeof(int);
+    const size_t per_set = sizeof(double) * ((4 + 2 * GORT_NLAYERS + LUT_NSP) * LUT_ZW + LUT_SHP) + 2 * sizeof(int);
     char *base = (char *) workspace(ctx, per_set * (size_t) chunk + 256);
     if (!base) return GORT_ERR_NOMEM;
     LutWork w;
@@ -869,7 +908,8 @@ int launch_lut_dead(gort_ctx *ctx, cudaStream_t s, int n_sets, const double *str
     w.vg = w.trig + (size_t) chunk * 4 * LUT_ZW;
     w.tube = w.vg + (size_t) chunk * GORT_NLAYERS * LUT_ZW;
     w.es_all = w.tube + (size_t) chunk * LUT_NSP * LUT_ZW;
-    w.head = (int *) (w.es_all + (size_t) chunk * GORT_NLAYERS * LUT_ZW);
+    w.shp = w.es_all + (size_t) chunk * GORT_NLAYERS * LUT_ZW;
+    w.head = (int *) (w.shp + (size_t) chunk * LUT_SHP);
     w.sub = w.head + chunk;
     const size_t N = (size_t) n_sets;
     for (int m0 = 0; m0 < n_sets; m0 += chunk) {
@@ -905,7 +945,7 @@ int launch_lut(gort_ctx *ctx, cudaStream_t s, int n_sets, const double *structur
     }
     const int chunk = n_sets < LUT_CHUNK ? n_sets : LUT_CHUNK;
     // workspace of one pass
-    const size_t per_set = sizeof(double) * (4 + GORT_NLAYERS + LUT_NSP) * LUT_ZW + 2 * sizeof(int);
+    const size_t per_set = sizeof(double) * ((4 + GORT_NLAYERS + LUT_NSP) * LUT_ZW + LUT_SHP) + 2 * sizeof(int);
     char *base = (char *) workspace(ctx, per_set * (size_t) chunk + 256);
     if (!base) return GORT_ERR_NOMEM;
     LutWork w;
@@ -913,7 +953,8 @@ int launch_lut(gort_ctx *ctx, cudaStream_t s, int n_sets, const double *structur
     w.vg = w.trig + (size_t) chunk * 4 * LUT_ZW;
     w.tube = w.vg + (size_t) chunk * GORT_NLAYERS * LUT_ZW;
     w.es_all = NULL;
-    w.head = (int *) (w.tube + (size_t) chunk * LUT_NSP * LUT_ZW);
+    w.shp = w.tube + (size_t) chunk * LUT_NSP * LUT_ZW;
+    w.head = (int *) (w.shp + (size_t) chunk * LUT_SHP);
     w.sub = w.head + chunk;
     const size_t N = (size_t) n_sets;
     for (int m0 = 0; m0 < n_sets; m0 += chunk) {

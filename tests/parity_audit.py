@@ -37,6 +37,9 @@ COND_FACTOR = 32.0
 # the 1-ULP libm moves a given call with probability 1/2 per seed: the K proportions (differences of O(1) areal
 # proportions, cheap to evaluate) get enough seeds that a single critical call is all but certainly exercised
 K_SEEDS = tuple(range(1, 13))
+# a histogram-bin flip needs one particular libm call moved in one particular direction (probability 1/4 per seed): the LUT
+# conditioning, measured only for the few records that have an entry beyond the tolerance, takes 24 seeds
+LUT_SEEDS = tuple(range(1, 25))
 
 _G = {}          # arrays inherited by the forked workers (set before the pool is created)
 
@@ -155,7 +158,7 @@ def _lut_job(st6, lut_gpu, direct_ref=False):
     lut_o = o.lut(st6)
     first = _lut_columns(lut_gpu, lut_o, None)
     if any(v["n_beyond_tol"] for v in first.values()):
-        sens = checkers.sensitivity(lambda c: c.lut(st6), lut_o)
+        sens = checkers.sensitivity(lambda c: c.lut(st6), lut_o, seeds=LUT_SEEDS)
         first = _lut_columns(lut_gpu, lut_o, sens)
     if direct_ref and checkers.ref() is not None:
         lut_r = checkers.ref().lut(st6)
@@ -255,7 +258,7 @@ def _pick(rng, n_total, n, forced=()):
 # the audit
 # ---------------------------------------------------------------------------------------------------
 # c2_lines 0 = the whole sweep; *_total / c5_grid shrink the workload itself (CPU self-test of this module only)
-DEFAULT_SIZES = {"c2_lines": 0, "c3_sets": 512, "c4_members": 2048, "c5_sets": 2048,
+DEFAULT_SIZES = {"c2_lines": 0, "c3_sets": 1024, "c4_members": 4096, "c5_sets": 4096,
                  "c3_total": 10000, "c4_total": 100000, "c5_grid": (8, 8, 4, 8, 8, 8)}
 BENCH_SIZES = {"c2_lines": 0, "c3_sets": 96, "c4_members": 512, "c5_sets": 512}
 

@@ -613,3 +613,23 @@ def test_component_signatures_through_the_bulk_store_ring(gort, nw, pitch):
         assert np.array_equal(r[:, :, nw:ncol], np.repeat(r[:, :, nw - 1:nw], ncol - nw, axis=2))
         assert np.array_equal(sc[:, :, nw:ncol], np.repeat(sc[:, :, nw - 1:nw], ncol - nw, axis=2))
     assert np.all(r[:, :, ncol:] == -9.0) and np.all(sc[:, :, ncol:] == -9.0)
+
+
+def test_host_api_leaves_padding_columns_of_pitched_rows_alone(gort):
+    """gort_brdf_batch with out_pitch > n_wl (host arrays): only the n_wl columns of every row are written."""
+    import ctypes as C
+    from gort_b200 import api
+    w = wk.c1_readme()
+    st, wl = w["structure"], np.arange(400.0, 2500.0, 30.0)              # 70 bands
+    ang = np.stack([np.linspace(0, 60, 50), np.zeros(50), np.full(50, 30.0), np.linspace(0, 300, 50)])
+    lut = gort.lut(st)
+    rl, tl, rs = gort.spectra(w["leaf"], w["soil"], wl)
+    dense, sc_dense = gort.brdf(st, lut, ang, rl[0], tl[0], rs[0], want_scomp=True)
+    P = 96
+    out = np.full((1, 50, P), -4.0); sc = np.full((1, 50, P, 4), -4.0)
+    sh = gort._shape(1, 50, wl.size, False, False, out_pitch=P)
+    a = [np.ascontiguousarray(x) for x in (st, lut, ang, rl[0], tl[0], rs[0])]
+    rc = gort._lib.gort_brdf_batch(gort._h, C.byref(sh), *[api._ptr(x) for x in a], api._ptr(out), api._ptr(sc), None)
+    assert rc == 0
+    assert np.array_equal(out[:, :, :70], dense) and np.all(out[:, :, 70:] == -4.0)
+    assert np.array_equal(sc[:, :, :70], sc_dense) and np.all(sc[:, :, 70:] == -4.0)
