@@ -62,29 +62,35 @@ __device__ __forceinline__ double right_ellipse_area(double r, double b, double 
 }
 
 // gortt_pn_kopen.c:170-229 with the "weird" section :233-282 inlined
-__device__ __noinline__ double cross_section(const Crown& c, const Ang& a, double h, double z)
+// (scalars by value: a noinline function taking the Crown / Ang structs by reference forces them into local memory --
+// ncu counted 292 MB of DRAM writes for an 82 MB result in the tube kernel)
+__device__ __noinline__ double cross_section_v(double r, double rr, double as, double ac, double at, double h, double z)
 {
-    if (z < h - c.r) return 0.0;
-    double h_low = h - c.r * a.s;
-    double h_high = h + c.r * a.s;
+    if (z < h - r) return 0.0;
+    double h_low = h - r * as;
+    double h_high = h + r * as;
     if (z <= h_low) {
-        double q = c.rr - (h - z) * (h - z);
+        double q = rr - (h - z) * (h - z);
         double r_p = (q <= 0) ? 0 : sqrt(q);
         return GORT_PI * r_p * r_p;
     } else if (z > h_low && z < h_high) {
         double zdiff = h - z;
-        double r_p = sqrt(c.rr - zdiff * zdiff);
-        double x_cc = zdiff * a.t;
-        double x_p = x_cc / (1.0 - a.c * a.c);
+        double r_p = sqrt(rr - zdiff * zdiff);
+        double x_cc = zdiff * at;
+        double x_p = x_cc / (1.0 - ac * ac);
         double a_cp = left_circle_area(r_p, x_p - x_cc);
-        double a_ep = right_ellipse_area(c.r, c.r * (1.0 / a.c), x_p);
+        double a_ep = right_ellipse_area(r, r * (1.0 / ac), x_p);
         return a_cp + a_ep;
     }
-    return GORT_PI * c.rr * (1.0 / a.c);
+    return GORT_PI * rr * (1.0 / ac);
+}
+__device__ __forceinline__ double cross_section(const Crown& c, const Ang& a, double h, double z)
+{
+    return cross_section_v(c.r, c.rr, a.s, a.c, a.t, h, z);
 }
 
 // gortt_pn_kopen.c:149-167
-__device__ __noinline__ double proj_volume(const Crown& c, const Ang& a, double h)
+__device__ __forceinline__ double proj_volume(const Crown& c, const Ang& a, double h)
 {
     double vol = 0.0;
     int guard = 0;
@@ -134,14 +140,13 @@ __device__ __forceinline__ double triang_fcn(double x, double b, double r, doubl
 // evaluated by Horner's rule (2 FMAs instead of the reference's 6 unfused operations; the absolute error stays
 // ~1e-16 r^2 as in the reference's own form, and the |a3| < 1e-10 clamp of :867 is applied to it the same way), and
 // f = (2 tan h i) sqrt(a3).  The reference's (double)(float) loop factors are small integers, exact in either type.
-__device__ __noinline__ double triang(double b, double r, const Ang& a)
+__device__ __noinline__ double triang(double b, double r, double sint, double cost, double tant)
 {
-    double sint = a.s, cost = a.c;
     double a1 = r * r - b * b * sint * sint;
     double x0 = b * (sint * sint) + sqrt(a1) * cost;
     const int m = LUT_NOINT;
     double h = .50 * (x0 - b) / (double) (float) m;
-    const double c0 = r * r - b * b, c1 = -2.0 * b * h, c2 = -(1.0 + a.t * a.t) * (h * h), d = 2.0 * a.t * h;
+    const double c0 = r * r - b * b, c1 = -2.0 * b * h, c2 = -(1.0 + tant * tant) * (h * h), d = 2.0 * tant * h;
     double sum1 = 0.0, sum2 = 0.0, f = 1.0;
 #pragma unroll 2
     for (int i = 0; i < m - 1; i++, f += 2.0) {
@@ -152,8 +157,8 @@ __device__ __noinline__ double triang(double b, double r, const Ang& a)
     sum1 += (d * f) * sqrt_clamped(fma(fma(c2, f, c1), f, c0));          // point 39
     double volume = 4.0 * sum1;
     volume += 2.0 * sum2;
-    volume += triang_fcn(x0, b, r, a.t);
-    volume += triang_fcn(b, b, r, a.t);
+    volume += triang_fcn(x0, b, r, tant);
+    volume += triang_fcn(b, b, r, tant);
     volume *= h / 3.0;
     return volume;
 }
@@ -167,12 +172,12 @@ __device__ __forceinline__ double sector(double a1, double a2, double r)
 }
 
 // gortt_pn_kopen.c:771-792
-__device__ __noinline__ double trisec(double hh, double hh_b, const Ang& a, double r)
+__device__ __forceinline__ double trisec(double hh, double hh_b, const Ang& a, double r)
 {
     double tmp = (hh - hh_b);
     double x = -1.0 * tmp * a.s + sqrt(r * r - tmp * tmp) * a.c;
     double b = -tmp / a.s;
-    return triang(b, r, a) + sector(x, r, r);
+    return triang(b, r, a.s, a.c, a.t) + sector(x, r, r);
 }
 
 // gortt_pn_kopen.c:876-886
@@ -216,7 +221,7 @@ __device__ __forceinline__ double cylind_to_r(double r, double h1, double h)
 }
 
 // gortt_pn_kopen.c:665-768; hp_h = height_p[h], hp_s = height_p[h_s]
-__device__ __noinline__ double tube_vol(const Crown& c, const Ang& a, double hp_h, double hp_s, double h_b)
+__device__ __forceinline__ double tube_vol(const Crown& c, const Ang& a, double hp_h, double hp_s, double h_b)
 {
     const double r = c.r;
     double V, V_sp1, V_sp2, V_cyln, h_t, h_tt;
@@ -269,7 +274,7 @@ __device__ __noinline__ double tube_vol(const Crown& c, const Ang& a, double hp_
 }
 
 // gortt_pn_kopen.c:566-645; hz = height_p[z]
-__device__ __noinline__ double mean_single_crown_path(const Crown& c, const Ang& a, double hz, double h)
+__device__ __forceinline__ double mean_single_crown_path(const Crown& c, const Ang& a, double hz, double h)
 {
     if (hz > h + c.r - 0.0001) return 0.0;
     if (hz < h - c.r + 0.0001) return 4.0 * c.r / 3.0;
@@ -286,7 +291,7 @@ __device__ __noinline__ double mean_single_crown_path(const Crown& c, const Ang&
 }
 
 // gortt_pn_kopen.c:534-563
-__device__ double expected_single_crown_path(const Crown& c, const Ang& a, double hz)
+__device__ __forceinline__ double expected_single_crown_path(const Crown& c, const Ang& a, double hz)
 {
     double ES = 0.0;
     double dh = (c.h2_p - c.h1_p) / (double) LUT_NH_ES;
@@ -626,9 +631,17 @@ lut_crown_kernel(int n, int m0, const double* __restrict__ structure, size_t N, 
             qn *= q;
             const double wgt = pw * c_inv_fact[nn];
             const double u = fma(-spd, qn, spd5);
-            const int idx = (int) u;
-            redo |= (fabs(u - rint(u)) < 1e-9) | ((unsigned) idx >= (unsigned) n_tab);
-            const int row = min(max(idx, 0), n_tab - 1);
+            // floor(u) and the distance of u from the nearest integer without the conversion unit (FRND / F2I run at a
+            // quarter of the FP64 rate and made this loop XU-bound: ncu 36 % XU against 45 % FP64): 0.5 <= u < 2^22, so
+            // u + 2^22 has the exponent of 2^22, its mantissa holds floor(u) above bit 30 and the fraction of u, in
+            // units of 2^-30 = 9.3e-10, below.  A fraction within 2 units of either end (|u - rint(u)| < 1.9e-9, a
+            // superset of the 1e-9 rule), a sum that left the binade (u >= 2^22, NaN) or a bin beyond the table raise
+            // the flag.
+            const long long ub = __double_as_longlong(u + 4194304.0);
+            const int idx = (int) ((ub >> 30) & 0x3fffff);
+            const int frac = (int) (ub & 0x3fffffff);
+            redo |= (frac < 2) | (frac > 0x3fffffff - 2) | ((ub >> 52) != 0x415) | (idx >= n_tab);
+            const int row = min(idx, n_tab - 1);
             // gortt_calc_epgap + gortt_calc_pgap, :1110-1114, :1138
 #pragma unroll
             for (int j = 0; j < SUB; j++) e_t[j] = fma(s_tab[j][row], wgt, e_t[j]);

@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """`ncu -i X.ncu-rep --page raw --csv | python tools/ncu_to_json.py "<how it was captured>" > profiles/r2_ncu_summary.json`
-Per kernel (the LAST launch of each name): duration, executed warp instructions, FP64 / XU pipe and issue utilisation,
+Per kernel (the LONGEST launch of each name): duration, executed warp instructions, FP64 / XU pipe and issue utilisation,
 warps active, DRAM bytes, launch shape.  bench.py quotes these as the kernels' executed work."""
 import csv, json, re, sys
 rows = list(csv.reader(sys.stdin))
@@ -32,8 +32,10 @@ for r in data:
             else:
                 v = v * f
             d[k] = round(v, 3)
+    if name.startswith("at::"):
+        continue                                   # torch's own fill / copy kernels are not ours
     base = re.sub(r"<.*$", "", name)
-    out[name] = d
-    out.setdefault(base, d)
-    out[base] = d if name == base else out[base]
+    for key in {name, base}:
+        if key not in out or d.get("duration_us", 0) > out[key].get("duration_us", 0):
+            out[key] = d
 print(json.dumps(out, indent=1))
