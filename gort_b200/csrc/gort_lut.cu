@@ -501,7 +501,8 @@ __device__ __forceinline__ Ang ang_load(const LutWork& w, int i, int t)
 __global__ void __launch_bounds__(LUT_VG_THREADS, 6)
 lut_vg_kernel(int n, int m0, const double* __restrict__ structure, size_t N, LutWork w)
 {
-    __shared__ double s_A[LUT_NA][LUT_VG_THREADS];
+    __shared__ double s_A[30][LUT_VG_THREADS];           // 14 + K <= 29 distinct cross-sections of this thread
+    __shared__ double s_zk[16][LUT_VG_THREADS];          // its crown-centre heights
     const long e = (long) blockIdx.x * blockDim.x + threadIdx.x;
     const int i = (int) (e / LUT_ZW), t = (int) (e - (long) i * LUT_ZW);
     if (i >= n || w.head[i] != i || t >= GORT_NTH) return;
@@ -509,14 +510,10 @@ lut_vg_kernel(int n, int m0, const double* __restrict__ structure, size_t N, Lut
     const Ang a = ang_load(w, i, t);
     double* vg = w.vg + (size_t) i * GORT_NLAYERS * LUT_ZW + t;
     // crown-centre heights of the midpoint rule, gortt_pn_kopen.c:162: a running sum
-    double zk[16];
     int K = 0;
-#pragma unroll
-    for (int k = 0; k < 16; k++) zk[k] = 0.0;
     {
         double z = S.c.h1_p + S.c.dz_p / 2.0;
-#pragma unroll
-        for (int k = 0; k < 16; k++) { if (z <= S.c.h2_p && K == k) { zk[k] = z; K = k + 1; z += S.c.dz_p; } }
+        for (; z <= S.c.h2_p && K < 16; z += S.c.dz_p) s_zk[K++][threadIdx.x] = z;
         if (K == 16 && z <= S.c.h2_p) K = 17;                    // more than 16 midpoints: the literal rule below
     }
     if (K < 1 || K >= 16) {
@@ -525,13 +522,10 @@ lut_vg_kernel(int n, int m0, const double* __restrict__ structure, size_t N, Lut
         return;
     }
     // distinct cross-sections j = 0 .. 13 + K: (h, z) = (0, K-1-j) for j < K, (j-K+1, 0) after
-    double zsel = 0.0;
 #pragma unroll 1
     for (int j = 0; j < GORT_NLAYERS + K - 1; j++) {
         const int ih = max(0, j - (K - 1)), k = ih - (j - (K - 1));
-#pragma unroll
-        for (int q = 0; q < 16; q++) if (q == k) zsel = zk[q];
-        s_A[j][threadIdx.x] = cross_section(S.c, a, layer_height_p(w, i, ih), zsel);
+        s_A[j][threadIdx.x] = cross_section(S.c, a, layer_height_p(w, i, ih), s_zk[k][threadIdx.x]);
     }
 #pragma unroll 1
     for (int h = 0; h < GORT_NLAYERS; h++) {
@@ -909,9 +903,7 @@ int launch_lut_dead(gort_ctx *ctx, cudaStream_t s, int n_sets, const double *str
                     double *t_open, double *dt_open, double *dk_open, double *k_open)
 {
     note_other_work(ctx);
-    int cap = n_sets / (ctx->sm_count * 12);
-    if (cap < 1) cap = 1;
-    if (cap > LUT_GROUP_CAP) cap = LUT_GROUP_CAP;
+    const int cap = LUT_GROUP_CAP;
     const int chunk = n_sets < LUT_CHUNK / 2 ? n_sets : LUT_CHUNK / 2;
     const size_t per_set = sizeof(double) * ((4 + 2 * GORT_NLAYERS + LUT_NSP) * LUT_ZW + LUT_SHP) + 2 * sizeof(int);
     char *base = (char *) workspace(ctx, per_set * (size_t) chunk + 256);
@@ -946,11 +938,10 @@ int launch_lut(gort_ctx *ctx, cudaStream_t s, int n_sets, const double *structur
         ctx->launches++;
         return check_cuda(ctx, cudaGetLastError(), "gort_lut launch");
     }
-    // group cap: as large as possible (the geometry is shared by the whole group) while the batch still yields
-    // enough groups to fill the GPU a few times over; results do not depend on it
-    int cap = n_sets / (ctx->sm_count * 12);
-    if (cap < 1) cap = 1;
-    if (cap > LUT_GROUP_CAP) cap = LUT_GROUP_CAP;
+    // group cap: the geometry is shared by the whole group; with the flat kernels the grid no longer depends on the
+    // number of groups, so the cap is simply the largest one (round 1's CTA-per-group kernel shrank it for small
+    // batches, which made a 16 384-set shard of the C5 grid do 7x the geometry work).  Results do not depend on it.
+    const int cap = LUT_GROUP_CAP;
     if (!ctx->lut_attr_set) {
         cudaError_t e = cudaFuncSetAttribute(lut_crown_kernel<LUT_SUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(CrownSmem<LUT_SUB>));
         if (e != cudaSuccess) return check_cuda(ctx, e, "lut_crown_kernel shared memory");

@@ -36,30 +36,39 @@ def main():
     if args.limit:
         st = np.ascontiguousarray(st[:, :args.limit])
     M = st.shape[1]
-    from .parallel import shard_range
+    from .parallel import lut_generate_pipelined, pipelined_blocks, shard_range
     ts = torch.cuda.Stream(device=dev)                   # created once, outside the timed region
-    lo, hi = shard_range(M, rank, world)
-    d_blk = torch.from_numpy(np.ascontiguousarray(st[:, lo:hi])).to(dev)      # this rank's structure block: resident before timing
-    d_loc = torch.empty((hi - lo, LUT_STRIDE), dtype=torch.float64, device=dev)
     method = LUT_Q08 if args.q08 else LUT_FULL
-
-    def compute_local(block):
-        # `block` is st[:, lo:hi] (lut_generate_sharded slices it the same way); the device copy is already there
-        with torch.cuda.stream(ts):
-            g.lut_dev(d_blk, d_loc, method, stream=ts.cuda_stream)
-        return d_loc
-
-    # warm-up outside the timed region: CUDA module load, and NCCL's lazily created communicator
-    with torch.cuda.stream(ts):
-        lut_generate_sharded(st, compute_local, rank, world)
-    torch.cuda.synchronize()
-    if world > 1:
-        torch.distributed.barrier()
+    n_sub = 4 if pipelined_blocks(M, rank, world, 4) is not None else 0
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-    with torch.cuda.stream(ts):
-        e0.record(ts)
-        luts = lut_generate_sharded(st, compute_local, rank, world)      # kernels, then ONE all_gather_into_tensor on the same stream
-        e1.record(ts)
+    if n_sub:
+        # the grid in 4 super-blocks, each split over the ranks: the all-gather of one runs under the kernels of the next
+        with torch.cuda.stream(ts):
+            luts, d_blocks = lut_generate_pipelined(st, g, rank, world, dev, n_sub=n_sub, method=method, compute_stream=ts)   # warm-up
+            torch.cuda.synchronize()
+            if world > 1:
+                torch.distributed.barrier()
+            e0.record(ts)
+            luts, d_blocks = lut_generate_pipelined(st, g, rank, world, dev, n_sub=n_sub, method=method, compute_stream=ts, d_blocks=d_blocks)
+            e1.record(ts)
+    else:
+        lo, hi = shard_range(M, rank, world)
+        d_blk = torch.from_numpy(np.ascontiguousarray(st[:, lo:hi])).to(dev)      # this rank's structure block: resident before timing
+        d_loc = torch.empty((hi - lo, LUT_STRIDE), dtype=torch.float64, device=dev)
+
+        def compute_local(block):
+            with torch.cuda.stream(ts):
+                g.lut_dev(d_blk, d_loc, method, stream=ts.cuda_stream)
+            return d_loc
+
+        with torch.cuda.stream(ts):
+            lut_generate_sharded(st, compute_local, rank, world)              # warm-up: module load, NCCL communicator
+            torch.cuda.synchronize()
+            if world > 1:
+                torch.distributed.barrier()
+            e0.record(ts)
+            luts = lut_generate_sharded(st, compute_local, rank, world)       # kernels, then ONE all_gather_into_tensor
+            e1.record(ts)
     torch.cuda.synchronize()
     dt = torch.tensor([e0.elapsed_time(e1) * 1e-3], dtype=torch.float64, device=dev)
     if world > 1:

@@ -85,6 +85,52 @@ def lut_generate_sharded(structure, compute_local, rank, world, device=None):
     return allgather_rows(local, M, rank, world)
 
 
+def pipelined_blocks(n_total, rank, world, n_sub):
+    """Block layout for LUT generation with the all-gather hidden under the kernels: the n_total parameter sets are cut
+    into n_sub super-blocks, each super-block is split over the ranks in equal pieces.  Gathering piece j of every rank
+    fills super-block j of the assembled array in natural order, so the gather of super-block j can run while the
+    kernels of super-block j+1 do.  Returns [(lo, hi)] of this rank's piece in every super-block, or None if the sizes
+    do not divide evenly."""
+    if n_sub < 1 or n_total % (n_sub * world) != 0:
+        return None
+    piece = n_total // (n_sub * world)
+    return [(j * piece * world + rank * piece, j * piece * world + (rank + 1) * piece) for j in range(n_sub)]
+
+
+def lut_generate_pipelined(structure, gort, rank, world, device, n_sub=4, method=0, compute_stream=None, d_blocks=None):
+    """LUTs of all M sets on every rank (GPU only): kernels of super-block j+1 on `compute_stream` while one NCCL
+    all-gather assembles super-block j on a second stream.  Returns (assembled [M][184] tensor, d_blocks) -- pass
+    d_blocks back in to reuse the device copies of this rank's structure pieces."""
+    M = structure.shape[1]
+    blocks = pipelined_blocks(M, rank, world, n_sub)
+    assert blocks is not None, "M must divide by n_sub * world"
+    cs = compute_stream or torch.cuda.current_stream()
+    if d_blocks is None:
+        d_blocks = [torch.from_numpy(np.ascontiguousarray(structure[:, lo:hi])).to(device) for lo, hi in blocks]
+    piece = blocks[0][1] - blocks[0][0]
+    out = torch.empty((M, LUT_STRIDE), dtype=torch.float64, device=device)
+    loc = [torch.empty((piece, LUT_STRIDE), dtype=torch.float64, device=device) for _ in range(n_sub)]
+    gs = getattr(lut_generate_pipelined, "_gather_stream", None)
+    if gs is None or gs.device != torch.device(device):
+        gs = torch.cuda.Stream(device=device)
+        lut_generate_pipelined._gather_stream = gs
+    gs.wait_stream(cs)                                  # `out` and `loc` were allocated on the compute stream
+    for j in range(n_sub):
+        gort.lut_dev(d_blocks[j], loc[j], method, stream=cs.cuda_stream)
+        ev = torch.cuda.Event()
+        ev.record(cs)
+        with torch.cuda.stream(gs):
+            gs.wait_event(ev)
+            if world > 1:
+                dist.all_gather_into_tensor(out[j * piece * world:(j + 1) * piece * world], loc[j])
+            else:
+                out[j * piece:(j + 1) * piece].copy_(loc[j], non_blocking=True)
+    cs.wait_stream(gs)
+    for t in loc:
+        t.record_stream(gs)
+    return out, d_blocks
+
+
 def write_lut_directory(luts, out_dir, names=None):
     """Rank 0: one "-W"-layout text file per parameter set (gortt.c:123-128), readable by `gortt -P`."""
     out_dir = Path(out_dir)

@@ -17,7 +17,7 @@ ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tests"))
 
-from gort_b200.parallel import allgather_rows, lut_generate_sharded, shard_counts, shard_range  # noqa: E402
+from gort_b200.parallel import allgather_rows, lut_generate_sharded, pipelined_blocks, shard_counts, shard_range  # noqa: E402
 from gort_b200 import workloads as wk  # noqa: E402
 
 
@@ -30,6 +30,16 @@ def test_shard_range_partitions():
             sizes = [b[1] - b[0] for b in blocks]
             assert max(sizes) - min(sizes) <= 1 and sizes == sorted(sizes, reverse=True)
             assert sizes == shard_counts(n, world)
+
+
+def test_pipelined_blocks_tile_the_grid_in_gather_order():
+    """super-block j = the pieces of ranks 0..world-1 in order: gathering piece j of every rank fills a contiguous range"""
+    for M, world, n_sub in ((131072, 2, 4), (131072, 8, 4), (96, 3, 2), (64, 1, 4)):
+        order = [pipelined_blocks(M, r, world, n_sub)[j] for j in range(n_sub) for r in range(world)]
+        assert order[0][0] == 0 and order[-1][1] == M
+        assert all(order[i][1] == order[i + 1][0] for i in range(len(order) - 1))
+        assert len({b[1] - b[0] for b in order}) == 1
+    assert pipelined_blocks(100, 0, 3, 4) is None
 
 
 def _free_port():
