@@ -566,8 +566,8 @@ def multi_gpu_extras(g, torch, dist, dev, ts, rank, world, args):
     res["c5_lut_allgather"] = {
         "luts": M, "luts_per_rank": hi - lo, "kernel_ms": kern_ms, "allgather_ms": gather_ms, "total_ms": total_ms,
         "pipelined_total_ms": pipe_ms, "pipelined_super_blocks": n_sub,
-        "luts_per_s": M / (pipe_ms * 1e-3), "one_gpu_kernel_ms": one_ms, "speedup_vs_one_gpu": one_ms / pipe_ms,
-        "speedup_vs_one_gpu_unpipelined": one_ms / total_ms,
+        "luts_per_s": M / (min(total_ms, pipe_ms) * 1e-3), "one_gpu_kernel_ms": one_ms,
+        "speedup_vs_one_gpu": one_ms / min(total_ms, pipe_ms), "speedup_vs_one_gpu_pipelined": one_ms / pipe_ms,
         "allgather_bytes_total": bytes_total, "allgather_bytes_received_per_rank": bytes_total * (world - 1) // world,
         "allgather_gbs_per_rank": bytes_total * (world - 1) / world / (gather_ms * 1e-3) / 1e9,
         "assembled_equals_one_gpu_bits_on_every_rank": bool(flag.item() == 1.0),

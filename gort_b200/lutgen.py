@@ -25,6 +25,9 @@ def main():
     ap.add_argument("--out", default=None, help="directory for the -W layout text files (rank 0)")
     ap.add_argument("--limit", type=int, default=0, help="only the first N grid points")
     ap.add_argument("--q08", action="store_true")
+    ap.add_argument("--pipelined", action="store_true",
+                    help="grid in 4 super-blocks, the all-gather of one under the kernels of the next (pays only when a rank's "
+                         "share is several tens of thousands of sets: measured slower than kernels + one all-gather for C5 on 8 GPUs)")
     ap.add_argument("--write-max", type=int, default=4096, help="cap on the number of text files written")
     args = ap.parse_args()
 
@@ -39,7 +42,7 @@ def main():
     from .parallel import lut_generate_pipelined, pipelined_blocks, shard_range
     ts = torch.cuda.Stream(device=dev)                   # created once, outside the timed region
     method = LUT_Q08 if args.q08 else LUT_FULL
-    n_sub = 4 if pipelined_blocks(M, rank, world, 4) is not None else 0
+    n_sub = 4 if args.pipelined and pipelined_blocks(M, rank, world, 4) is not None else 0
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     if n_sub:
         # the grid in 4 super-blocks, each split over the ranks: the all-gather of one runs under the kernels of the next
