@@ -178,9 +178,20 @@ rsurf_wide_kernel(const WideArgs a)
         }
     };
 
-    if (line_begin < line_end && (a.pdl || TAB)) {
-        // prologue that does not depend on geom_kernel's line records: overlaps with it under PDL; with a per-call table
-        // the bulk copies are in flight while the records are staged
+    bool prefetched = false;      // the first stage's record copies were issued in the prologue
+    if (line_begin < line_end) {
+        // Prologue that does not depend on geom_kernel's line records: under PDL it overlaps with that grid.  In plain
+        // stream order (the geometry kernel is complete: every flag is set, no acquire needed) the asynchronous copies of
+        // the first stage's records are issued first, so that they are in flight while the (set, lambda) table is built.
+        if (!a.pdl) {
+            const int nl0 = (int) min((long) STAGE, line_end - line_begin);
+            const double2* g = reinterpret_cast<const double2*>(a.rec + (size_t) line_begin * GORT_REC_STRIDE);
+            const unsigned sbase = (unsigned) __cvta_generic_to_shared(srec);
+            for (int i = tid; i < nl0 * 8; i += nthr)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(sbase + 16u * i), "l"(g + i) : "memory");
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            prefetched = true;
+        }
         fill_leaf(m);
         leaf_ready = true;
     }
@@ -221,11 +232,13 @@ rsurf_wide_kernel(const WideArgs a)
             __syncthreads();
             if (s_fault) break;                                   // the records never arrived: store nothing
             if (s0 == line_begin) WIDE_TL(2);                     // geometry records of the first stage ready
-            const double2* g = reinterpret_cast<const double2*>(a.rec + (size_t) s0 * GORT_REC_STRIDE);
-            const unsigned sbase = (unsigned) __cvta_generic_to_shared(srec);
-            for (int i = tid; i < nl * 8; i += nthr)
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(sbase + 16u * i), "l"(g + i) : "memory");
-            asm volatile("cp.async.commit_group;" ::: "memory");
+            if (!(prefetched && s0 == line_begin)) {
+                const double2* g = reinterpret_cast<const double2*>(a.rec + (size_t) s0 * GORT_REC_STRIDE);
+                const unsigned sbase = (unsigned) __cvta_generic_to_shared(srec);
+                for (int i = tid; i < nl * 8; i += nthr)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(sbase + 16u * i), "l"(g + i) : "memory");
+                asm volatile("cp.async.commit_group;" ::: "memory");
+            }
             asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
         __syncthreads();
