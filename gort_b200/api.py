@@ -59,7 +59,7 @@ ABI_SYMBOLS = [
     "gort_lut_batch", "gort_lut_batch_dev", "gort_spectra_batch", "gort_spectra_batch_dev",
     "gort_prospect_batch", "gort_brdf_batch", "gort_brdf_batch_dev", "gort_energy_batch",
     "gort_energy_batch_dev", "gort_gauleg", "gort_lut_write_text", "gort_lut_read_text",
-    "gort_dfma_peak", "gort_profile_begin", "gort_profile_end", "gort_set_overlap",
+    "gort_dfma_peak", "gort_profile_begin", "gort_profile_end", "gort_set_overlap", "gort_kernel_stamps_enable", "gort_kernel_stamps",
     "gort_forward_batch", "gort_jacobian_batch", "gort_lut_intermediates_batch", "gort_lut_intermediates_batch_dev", "gort_host_alloc_near", "gort_host_alloc_on_cpus", "gort_host_placement", "gort_soil_table_read", "gort_soil_from_table", "gort_soil_from_table_dev",
 ]
 
@@ -83,6 +83,8 @@ def load_library():
     lib.gort_stream.restype = vp
     lib.gort_synchronize.argtypes = [vp]
     lib.gort_set_overlap.argtypes = [vp, C.c_int]
+    lib.gort_kernel_stamps_enable.argtypes = [vp, C.c_int]
+    lib.gort_kernel_stamps.argtypes = [vp, _dp, _dp, _dp, C.POINTER(C.c_int)]
     lib.gort_soil_table_read.argtypes = [C.c_char_p, vp, C.c_char_p, C.c_size_t]
     lib.gort_soil_from_table.argtypes = [vp, vp, C.c_int, C.c_int, vp, vp]
     lib.gort_soil_from_table_dev.argtypes = [vp, vp, vp, C.c_int, C.c_int, vp, vp]
@@ -235,6 +237,15 @@ class Gort:
         g = C.c_double(); r = C.c_double(); n = C.c_int()
         self._check(self._lib.gort_profile_end(self._h, C.byref(g), C.byref(r), C.byref(n)))
         return g.value, r.value, n.value
+
+    def kernel_stamps_enable(self, enable=True):
+        self._check(self._lib.gort_kernel_stamps_enable(self._h, int(bool(enable))))
+
+    def kernel_stamps(self):
+        """-> dict: in-kernel span (first CTA entry to last CTA exit), mean per-CTA start-up and store phase [us], CTAs"""
+        a = C.c_double(); b = C.c_double(); c = C.c_double(); n = C.c_int()
+        self._check(self._lib.gort_kernel_stamps(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(n)))
+        return {"span_us": a.value, "startup_us_per_cta": b.value, "store_phase_us_per_cta": c.value, "ctas": n.value}
 
     def gauleg(self):
         x = np.empty(32); w = np.empty(32)

@@ -753,6 +753,20 @@ int gort_dfma_peak(gort_ctx *ctx, double *tflops)
     return launch_dfma_peak(ctx, ctx->stream, tflops);
 }
 
+int gort_kernel_stamps_enable(gort_ctx *ctx, int enable)
+{
+    if (!ctx) return GORT_ERR_INVALID;
+    ctx->stamps_on = enable ? 1 : 0;
+    return GORT_OK;
+}
+
+int gort_kernel_stamps(gort_ctx *ctx, double *span_us, double *startup_us, double *store_us, int *n_cta)
+{
+    if (!ctx) return GORT_ERR_INVALID;
+    TRYCUDA(ctx, cudaSetDevice(ctx->device), "cudaSetDevice");
+    return read_kernel_stamps(ctx, span_us, startup_us, store_us, n_cta);
+}
+
 int gort_profile_begin(gort_ctx *ctx, int max_steps)
 {
     if (!ctx || max_steps <= 0) return GORT_ERR_INVALID;

@@ -215,7 +215,7 @@ rsurf_flat_kernel(int n_sets, int n_geom, int n_wl, int spectra_per_set, long pi
 // summarised on stderr.
 static unsigned long long *timeline_half(gort_ctx *ctx, unsigned long long epoch)
 {
-    if (!ctx->dbg_timeline) return NULL;
+    if (!ctx->dbg_timeline && !ctx->stamps_on) return NULL;
     if (!ctx->d_timeline && cudaMalloc((void **) &ctx->d_timeline, 2 * 64 * GORT_MAX_WIDE_CTAS) != cudaSuccess) return NULL;
     return ctx->d_timeline + (epoch & 1) * 8 * GORT_MAX_WIDE_CTAS;
 }
@@ -246,6 +246,33 @@ static void timeline_report(gort_ctx *ctx, cudaStream_t s, int ncta, int half, c
     for (int i = 0; i < ncta; i++) { gw += (h[i * 8 + 4] - h[i * 8 + 3]) * 1e-3; st += (h[i * 8 + 3] - h[i * 8]) * 1e-3; run += (h[i * 8 + 5] - h[i * 8 + 4]) * 1e-3; }
     fprintf(stderr, "  per CTA: start-up %.2f us, gate wait %.2f us, store phase %.2f us\n", st / ncta, gw / ncta, run / ncta);
     free(h); free(prev);
+}
+
+// gort_kernel_stamps: in-kernel %globaltimer view of the most recent per-wavelength launch
+int read_kernel_stamps(gort_ctx *ctx, double *span_us, double *startup_us, double *store_us, int *n_cta)
+{
+    if (!ctx->d_timeline || ctx->stamps_ncta <= 0) return set_error(ctx, GORT_ERR_INVALID, "gort_kernel_stamps: no stamped launch yet");
+    cudaError_t e = cudaStreamSynchronize(ctx->stamps_stream);
+    if (e != cudaSuccess) return check_cuda(ctx, e, "gort_kernel_stamps");
+    const int n = ctx->stamps_ncta;
+    unsigned long long *h = (unsigned long long *) malloc(64 * (size_t) n);
+    if (!h) return set_error(ctx, GORT_ERR_NOMEM, "out of host memory");
+    e = cudaMemcpy(h, ctx->d_timeline + ctx->stamps_half * 8 * GORT_MAX_WIDE_CTAS, 64 * (size_t) n, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { free(h); return check_cuda(ctx, e, "gort_kernel_stamps"); }
+    unsigned long long first = ~0ull, last = 0;
+    double st = 0, run = 0;
+    for (int i = 0; i < n; i++) {
+        if (h[i * 8] < first) first = h[i * 8];
+        if (h[i * 8 + 5] > last) last = h[i * 8 + 5];
+        st += (double) (h[i * 8 + 4] - h[i * 8]) * 1e-3;          // entry -> gate passed (first store follows)
+        run += (double) (h[i * 8 + 5] - h[i * 8 + 4]) * 1e-3;     // gate passed -> all stores complete
+    }
+    free(h);
+    if (span_us) *span_us = (double) (last - first) * 1e-3;
+    if (startup_us) *startup_us = st / n;
+    if (store_us) *store_us = run / n;
+    if (n_cta) *n_cta = n;
+    return GORT_OK;
 }
 
 // what launch_brdf hands to the per-wavelength launchers
@@ -343,6 +370,7 @@ static int launch_wide(gort_ctx *ctx, cudaStream_t s, const gort_shape &sh, cons
     a.tl = timeline_half(ctx, a.epoch);
     a.wait_target = pl.gate ? a.epoch - 1 : 0;
     cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a);
+    if (a.tl) { ctx->stamps_ncta = n_chunks * (int) nby; ctx->stamps_half = (int) (a.epoch & 1); ctx->stamps_stream = s; }
     if (a.tl) timeline_report(ctx, s, n_chunks * (int) nby, (int) (a.epoch & 1), "rsurf_wide_kernel");
     return check_cuda(ctx, e, "rsurf_wide_kernel launch");
 }
@@ -505,7 +533,7 @@ int launch_brdf(gort_ctx *ctx, cudaStream_t s, const gort_shape &sh, const doubl
     bool same = ctx->last_was_wide != 0;
     for (int k = 0; k < 8; k++) same &= sig[k] == ctx->last_sig[k];
     for (int k = 0; k < 8; k++) ctx->last_sig[k] = sig[k];
-    const bool early_geom = ctx->overlap && use_pdl && !ev && same && !alias && sh.n_wl >= 64;
+    const bool early_geom = ctx->overlap && use_pdl && !ev && !ctx->stamps_on && same && !alias && sh.n_wl >= 64;
     {
         // the per-wavelength kernel that follows needs a large shared-memory carve-out; an SM only changes its
         // carve-out when idle, so ask for the same one here or the dependent kernel's CTAs could not join this
@@ -552,7 +580,7 @@ int launch_brdf(gort_ctx *ctx, cudaStream_t s, const gort_shape &sh, const doubl
         // are being recorded (an event between the two launches would time the overlap)
         BrdfPlan pl;
         pl.L = L; pl.rec = rec; pl.flags = ctx->d_flags[bi];
-        pl.pdl = use_pdl && !ev;
+        pl.pdl = use_pdl && !ev && !ctx->stamps_on;      // events or stamps: plain stream order, so that a launch is separable
         pl.gate = early_geom;
         pl.table = rs.ok ? NULL : table; pl.tab_ncol = tab_ncol; pl.tab_flag_base = (long) geom_tiles;
         int rc;

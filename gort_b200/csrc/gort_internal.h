@@ -53,6 +53,8 @@ struct gort_ctx {
     int dbg_no_pdl, dbg_no_tma, dbg_rows_on, dbg_timeline, dbg_rows, dbg_table_on;
     unsigned long long *d_timeline;
     int timeline_calls;
+    int stamps_on, stamps_ncta, stamps_half;       // gort_kernel_stamps
+    cudaStream_t stamps_stream;
     // pinned-buffer placement (gort_host_alloc_near): probed once
     int near_probed, near_ncpu;
     int near_cpu[1024];
@@ -92,6 +94,7 @@ int launch_prospect_full(gort_ctx *ctx, cudaStream_t s, int n_sets, const double
 int launch_jac_perturb(gort_ctx *ctx, cudaStream_t s, int n_sets, int row, double factor, const double *st_in, double *st_out);
 int launch_jac_diff(gort_ctx *ctx, cudaStream_t s, int n_sets, long per_set, int row, int lai, double h, const double *st,
                     const double *fp, const double *fm, double *jac);
+int read_kernel_stamps(gort_ctx *ctx, double *span_us, double *startup_us, double *store_us, int *n_cta);
 int launch_gauleg(gort_ctx *ctx, cudaStream_t s, double *d_out /*[2][32]*/);
 int launch_tav_tables(gort_ctx *ctx, cudaStream_t s, double *d_prospect);
 int upload_soil_tables(gort_ctx *ctx, cudaStream_t s, double *d_soil);

@@ -249,6 +249,16 @@ int gort_dfma_peak(gort_ctx *ctx, double *tflops);
 int gort_profile_begin(gort_ctx *ctx, int max_steps);
 int gort_profile_end(gort_ctx *ctx, double *geom_ms, double *rsurf_ms, int *n_steps);
 
+/* In-kernel view of the per-wavelength kernel (W >= 64): with stamps enabled every CTA of the kernel records
+ * %globaltimer at its phase boundaries (a store of 8 bytes per phase by one thread: no measurable cost); while stamps are
+ * enabled BRDF calls run in plain stream order (no overlap between kernels or calls), so that a launch is separable.
+ * gort_kernel_stamps synchronises the launching stream and returns, for the most recent such launch: the span from the
+ * first CTA's first instruction to the last CTA's last completed store, and the per-CTA means of the start-up (entry to
+ * first store) and store phases, in microseconds.  CUDA events around a launch additionally contain the launch and
+ * completion latency outside any CTA; the difference is what a roofline fraction taken from event times cannot show. */
+int gort_kernel_stamps_enable(gort_ctx *ctx, int enable);
+int gort_kernel_stamps(gort_ctx *ctx, double *span_us, double *startup_us, double *store_us, int *n_cta);
+
 #ifdef __cplusplus
 }
 #endif
