@@ -569,6 +569,37 @@ def multi_gpu_extras(g, torch, dist, dev, ts, rank, world, args):
     tp = torch.tensor([pipe_best], dtype=torch.float64, device=dev)
     dist.all_reduce(tp, op=dist.ReduceOp.MAX)
     pipe_ms = float(tp.item())
+    # the same with NO collective: every rank's kernels store their rows into every rank's table while they compute
+    # (gort_lut_batch_scatter_dev over symmetric memory: per-peer NVLink addresses, and the NVSwitch multicast address
+    # when there is one), a device-side barrier of the ranks before and after, all inside the timed region
+    from gort_b200.parallel import PeerLutTable, lut_generate_peer
+    peer = {}
+    try:
+        tab = PeerLutTable(M, dev)
+    except Exception as e:      # the platform refused symmetric memory (no fabric / fd handle exchange): say so, keep NCCL
+        tab, peer = None, {"unavailable": "%s: %s" % (type(e).__name__, str(e).splitlines()[0] if str(e) else "")}
+    d_peer = {}
+    if tab is not None:
+        modes = [("peer", False)] + ([("multicast", True)] if tab.multicast_ptr else [])
+        for name, mc in modes:
+            with torch.cuda.stream(ts):
+                tab.table.zero_()
+            dist.barrier(); torch.cuda.synchronize()
+            bestp = None
+            for k in range(4):
+                dist.barrier(); torch.cuda.synchronize()
+                pa_, pb_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                pa_.record(ts)
+                lut_generate_peer(d_blk, tab, g, ts, multicast=mc)
+                pb_.record(ts)
+                pb_.synchronize()
+                if k:
+                    bestp = pa_.elapsed_time(pb_) if bestp is None else min(bestp, pa_.elapsed_time(pb_))
+            tq = torch.tensor([bestp], dtype=torch.float64, device=dev)
+            dist.all_reduce(tq, op=dist.ReduceOp.MAX)
+            peer[name + "_total_ms"] = float(tq.item())
+            dist.barrier(); torch.cuda.synchronize()
+            d_peer[name] = tab.table.clone()
     # one GPU computing the whole grid: the reference bits and the 1-GPU kernel time
     d_full = T(st)
     d_one = torch.empty((M, LUT_STRIDE), dtype=torch.float64, device=dev)
@@ -576,21 +607,31 @@ def multi_gpu_extras(g, torch, dist, dev, ts, rank, world, args):
     ts.synchronize()
     same = bool(torch.equal(torch.nan_to_num(d_all, nan=-7.0), torch.nan_to_num(d_one, nan=-7.0)) and
                 torch.equal(torch.nan_to_num(d_pipe, nan=-7.0), torch.nan_to_num(d_one, nan=-7.0)))
+    for name, t_ in d_peer.items():
+        same = same and bool(torch.equal(torch.nan_to_num(t_, nan=-7.0), torch.nan_to_num(d_one, nan=-7.0)))
     flag = torch.tensor([1.0 if same else 0.0], dtype=torch.float64, device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if flag.item() != 1.0:
+        raise SystemExit("bench: a multi-GPU assembly of the C5 grid differs from the bits one GPU computes")
     bytes_total = M * LUT_STRIDE * 8
+    fused_ms = min([v for k_, v in peer.items() if k_.endswith("_total_ms")], default=None)
+    best_ms = min(x for x in (total_ms, pipe_ms, fused_ms) if x is not None)
     res["c5_lut_allgather"] = {
         "luts": M, "luts_per_rank": hi - lo, "kernel_ms": kern_ms, "allgather_ms": gather_ms, "total_ms": total_ms,
         "pipelined_total_ms": pipe_ms, "pipelined_super_blocks": n_sub,
-        "luts_per_s": M / (min(total_ms, pipe_ms) * 1e-3), "one_gpu_kernel_ms": one_ms,
-        "speedup_vs_one_gpu": one_ms / min(total_ms, pipe_ms), "speedup_vs_one_gpu_pipelined": one_ms / pipe_ms,
+        "peer_stores": peer, "best_total_ms": best_ms,
+        "luts_per_s": M / (best_ms * 1e-3), "one_gpu_kernel_ms": one_ms,
+        "speedup_vs_one_gpu": one_ms / best_ms, "speedup_vs_one_gpu_allgather": one_ms / total_ms,
+        "speedup_vs_one_gpu_pipelined": one_ms / pipe_ms,
         "allgather_bytes_total": bytes_total, "allgather_bytes_received_per_rank": bytes_total * (world - 1) // world,
         "allgather_gbs_per_rank": bytes_total * (world - 1) / world / (gather_ms * 1e-3) / 1e9,
         "assembled_equals_one_gpu_bits_on_every_rank": bool(flag.item() == 1.0),
         "timing": "CUDA events on the launching stream, best of 3 after a first pass, max over ranks; the structure blocks are "
                   "resident before the timed region.  kernel_ms / allgather_ms / total_ms: contiguous shards, kernels then ONE "
-                  "all-gather; pipelined_total_ms: the grid in super-blocks, the gather of one under the kernels of the next"}
-    del d_pipe, d_blocks
+                  "all-gather; pipelined_total_ms: the grid in super-blocks, the gather of one under the kernels of the next; "
+                  "peer_stores: no collective, the kernels that produce a row store it into every rank's table (per-peer "
+                  "NVLink addresses / the NVSwitch multicast address), barriers of the ranks inside the timed region"}
+    del d_pipe, d_blocks, d_peer, tab
     del d_full, d_one, d_all, d_loc
 
     # ---- C2 strong scaling: one forest, geometry blocks across ranks ----

@@ -56,7 +56,7 @@ _lib = None
 ABI_SYMBOLS = [
     "gort_create", "gort_destroy", "gort_last_error", "gort_stream", "gort_synchronize",
     "gort_device_count", "gort_host_alloc", "gort_host_free", "gort_launch_count",
-    "gort_lut_batch", "gort_lut_batch_dev", "gort_spectra_batch", "gort_spectra_batch_dev",
+    "gort_lut_batch", "gort_lut_batch_dev", "gort_lut_batch_scatter_dev", "gort_spectra_batch", "gort_spectra_batch_dev",
     "gort_prospect_batch", "gort_brdf_batch", "gort_brdf_batch_dev", "gort_energy_batch",
     "gort_energy_batch_dev", "gort_gauleg", "gort_lut_write_text", "gort_lut_read_text",
     "gort_dfma_peak", "gort_profile_begin", "gort_profile_end", "gort_set_overlap", "gort_kernel_stamps_enable", "gort_kernel_stamps",
@@ -102,6 +102,7 @@ def load_library():
     lib.gort_launch_count.restype = C.c_long
     lib.gort_lut_batch.argtypes = [vp, C.c_int, vp, C.c_int, vp]
     lib.gort_lut_batch_dev.argtypes = [vp, vp, C.c_int, vp, C.c_int, vp]
+    lib.gort_lut_batch_scatter_dev.argtypes = [vp, vp, C.c_int, vp, C.c_int, vp, C.c_int, C.POINTER(vp), C.c_int]
     lib.gort_lut_intermediates_batch.argtypes = [vp, C.c_int] + [vp] * 7
     lib.gort_lut_intermediates_batch_dev.argtypes = [vp, vp, C.c_int] + [vp] * 7
     lib.gort_spectra_batch.argtypes = [vp, C.c_int, vp, vp, C.c_double, C.c_double, C.c_int, vp, vp, vp, vp]
@@ -405,6 +406,14 @@ class Gort:
     def lut_dev(self, structure, out, method=LUT_FULL, stream=None):
         M = structure.shape[1]
         self._check(self._lib.gort_lut_batch_dev(self._h, stream, M, _ptr(structure), method, _ptr(out)))
+
+    def lut_scatter_dev(self, structure, out, dst_ptrs, method=LUT_FULL, multicast=False, stream=None):
+        """lut_dev, and the producing kernels also store every row at dst_ptrs[i] (raw device addresses of the same
+        block inside other tables: peer GPUs' memory mapped here, or NVSwitch multicast addresses)."""
+        M = structure.shape[1]
+        arr = (C.c_void_p * max(1, len(dst_ptrs)))(*[int(a) for a in dst_ptrs])
+        self._check(self._lib.gort_lut_batch_scatter_dev(self._h, stream, M, _ptr(structure), method, _ptr(out),
+                                                         len(dst_ptrs), arr, 1 if multicast else 0))
 
     def spectra_dev(self, leaf, soil, wavelength, rleaf, tleaf, rsoil, user_leaf=-1.0, user_soil=-1.0,
                     stream=None):

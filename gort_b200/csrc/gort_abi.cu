@@ -318,6 +318,19 @@ int gort_lut_batch_dev(gort_ctx *ctx, void *stream, int n_sets, const double *st
     return launch_lut(ctx, pick(ctx, stream), n_sets, structure, method, lut);
 }
 
+int gort_lut_batch_scatter_dev(gort_ctx *ctx, void *stream, int n_sets, const double *structure, int method,
+                               double *lut, int n_dst, double *const *dst, int multicast)
+{
+    if (!ctx) return GORT_ERR_INVALID;
+    if (!structure || !lut || n_sets <= 0 || n_dst < 0 || n_dst > GORT_LUT_MAX_DST || (n_dst > 0 && !dst))
+        return set_error(ctx, GORT_ERR_INVALID, "gort_lut_batch_scatter: bad arguments");
+    for (int q = 0; q < n_dst; q++)
+        if (!dst[q] || ((uintptr_t) dst[q] & 7)) return set_error(ctx, GORT_ERR_INVALID, "gort_lut_batch_scatter: destination %d is null or misaligned", q);
+    if (method != GORT_LUT_FULL && method != GORT_LUT_Q08) return set_error(ctx, GORT_ERR_INVALID, "gort_lut_batch: unknown method %d", method);
+    TRYCUDA(ctx, cudaSetDevice(ctx->device), "cudaSetDevice");
+    return launch_lut_out(ctx, pick(ctx, stream), n_sets, structure, method, lut, n_dst, dst, multicast != 0);
+}
+
 int gort_lut_batch(gort_ctx *ctx, int n_sets, const double *structure, int method, double *lut)
 {
     if (!ctx) return GORT_ERR_INVALID;

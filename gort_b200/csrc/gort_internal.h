@@ -84,6 +84,8 @@ int launch_energy(gort_ctx *ctx, cudaStream_t s, const gort_shape &sh, const dou
                   const double *lut, const double *angles, const double *rleaf, const double *tleaf,
                   const double *rsoil, double *albedo, double *favegt, double *fasoil);
 int launch_lut(gort_ctx *ctx, cudaStream_t s, int n_sets, const double *structure, int method, double *lut);
+int launch_lut_out(gort_ctx *ctx, cudaStream_t s, int n_sets, const double *structure, int method, double *lut,
+                   int n_dst, double *const *dst, int multicast);
 int launch_lut_dead(gort_ctx *ctx, cudaStream_t s, int n_sets, const double *structure, double *vb, double *fb,
                     double *t_open, double *dt_open, double *dk_open, double *k_open);
 int launch_spectra(gort_ctx *ctx, cudaStream_t s, int n_sets, const double *leaf, const double *soil,

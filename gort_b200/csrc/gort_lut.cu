@@ -552,6 +552,27 @@ lut_tube_kernel(int n, int m0, const double* __restrict__ structure, size_t N, L
 }
 
 // Crown-count loop and within-crown gap sums.  CTA = (sub-group head, zenith third), warp = entry height.
+// Where finished LUT rows go.  `local` is this GPU's copy (kopen_kernel reads the rows back from it); `dst` are further
+// copies of the same rows -- tables in the memory of peer GPUs mapped into this process (NVLink P2P), or one NVSwitch
+// multicast address that reaches every GPU of the group (`mc`: the store is then a multimem.st).  The rows leave with the
+// stores that produce them: posted writes over NVLink underneath the crown-count arithmetic of the other CTAs, instead of
+// an all-gather after the kernels.
+struct LutOut {
+    double* local;
+    int n, mc;
+    double* dst[GORT_LUT_MAX_DST];
+};
+
+__device__ __forceinline__ void lut_store(const LutOut& o, size_t off, double v)
+{
+    o.local[off] = v;
+    for (int q = 0; q < o.n; q++) {
+        double* a = o.dst[q] + off;
+        if (o.mc) asm volatile("multimem.st.relaxed.sys.global.f64 [%0], %1;" :: "l"(a), "d"(v) : "memory");
+        else *a = v;
+    }
+}
+
 template <int SUB>
 struct CrownSmem {
     double tab[SUB][LUT_TAB];                // exp(-s_bin tau') per member
@@ -560,7 +581,7 @@ struct CrownSmem {
 
 template <int SUB>
 __global__ void __launch_bounds__(32 * LUT_NSP, SUB == 1 ? 3 : 2)
-lut_crown_kernel(int n, int m0, const double* __restrict__ structure, size_t N, LutWork w, double* __restrict__ lut)
+lut_crown_kernel(int n, int m0, const double* __restrict__ structure, size_t N, LutWork w, const LutOut out)
 {
     extern __shared__ __align__(16) unsigned char crown_smem_raw[];
     CrownSmem<SUB>& sm = *reinterpret_cast<CrownSmem<SUB>*>(crown_smem_raw);
@@ -673,12 +694,12 @@ lut_crown_kernel(int n, int m0, const double* __restrict__ structure, size_t N, 
     // rows of the LUT record: p_n0[0][t] and epgap[0][t] (the 13 entry heights added in the reference's order, :457);
     // the openness factors are formed by kopen_kernel afterwards
     if (live) {
-        if (k == 0) for (int j = 0; j < nj; j++) lut[(size_t) (m + j) * GORT_LUT_STRIDE + t] = pn0_0;
+        if (k == 0) for (int j = 0; j < nj; j++) lut_store(out, (size_t) (m + j) * GORT_LUT_STRIDE + t, pn0_0);
         for (int j = k; j < nj; j += LUT_NSP) {
             double e = s_part[0][j][lane];
 #pragma unroll
             for (int q2 = 1; q2 < LUT_NSP; q2++) e += s_part[q2][j][lane];
-            lut[(size_t) (m + j) * GORT_LUT_STRIDE + GORT_NTH + t] = e;
+            lut_store(out, (size_t) (m + j) * GORT_LUT_STRIDE + GORT_NTH + t, e);
         }
     }
 }
@@ -875,13 +896,14 @@ lut_q08_kernel(int n_sets, const double* __restrict__ structure, double* __restr
 // zeniths, k_openep the same for epgap.  One warp per parameter set: the panels (f_i + f_{i-1})/2 * dth, i = 1..90,
 // three per lane, then a shuffle tree (the reference adds them left to right: same panels, different association).
 __global__ void __launch_bounds__(128)
-kopen_kernel(int n_sets, double* __restrict__ lut)
+kopen_kernel(int n_sets, const LutOut out)
 {
+    const double* lut = out.local;
     const int m = (int) (((long) blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     if (m >= n_sets) return;
     const int lane = threadIdx.x & 31;
     const double dth = 1 * GORT_PI / 180.0;
-    double* o = lut + (size_t) m * GORT_LUT_STRIDE;
+    const double* o = lut + (size_t) m * GORT_LUT_STRIDE;
     double ko = 0.0, ke = 0.0;
     for (int i = 1 + lane; i < GORT_NTH; i += 32) {
         double th1 = dth * (double) i, th0 = dth * (double) (i - 1);                 // gortt.c:783-787
@@ -896,7 +918,24 @@ kopen_kernel(int n_sets, double* __restrict__ lut)
         ko += __shfl_xor_sync(0xffffffffu, ko, off);
         ke += __shfl_xor_sync(0xffffffffu, ke, off);
     }
-    if (lane == 0) { o[2 * GORT_NTH] = ko; o[2 * GORT_NTH + 1] = ke; }
+    if (lane == 0) {
+        lut_store(out, (size_t) m * GORT_LUT_STRIDE + 2 * GORT_NTH, ko);
+        lut_store(out, (size_t) m * GORT_LUT_STRIDE + 2 * GORT_NTH + 1, ke);
+    }
+}
+
+// Rows that were produced locally only (the Q08 kernel) copied to the further destinations.
+__global__ void __launch_bounds__(256)
+lut_rows_out_kernel(size_t n_values, const LutOut out)
+{
+    for (size_t e = (size_t) blockIdx.x * blockDim.x + threadIdx.x; e < n_values; e += (size_t) gridDim.x * blockDim.x) {
+        const double v = out.local[e];
+        for (int q = 0; q < out.n; q++) {
+            double* a = out.dst[q] + e;
+            if (out.mc) asm volatile("multimem.st.relaxed.sys.global.f64 [%0], %1;" :: "l"(a), "d"(v) : "memory");
+            else *a = v;
+        }
+    }
 }
 
 int launch_lut_dead(gort_ctx *ctx, cudaStream_t s, int n_sets, const double *structure, double *vb, double *fb,
@@ -932,10 +971,25 @@ int launch_lut_dead(gort_ctx *ctx, cudaStream_t s, int n_sets, const double *str
 
 int launch_lut(gort_ctx *ctx, cudaStream_t s, int n_sets, const double *structure, int method, double *lut)
 {
+    return launch_lut_out(ctx, s, n_sets, structure, method, lut, 0, NULL, 0);
+}
+
+int launch_lut_out(gort_ctx *ctx, cudaStream_t s, int n_sets, const double *structure, int method, double *lut,
+                   int n_dst, double *const *dst, int multicast)
+{
     note_other_work(ctx);
+    LutOut out;
+    out.local = lut;
+    out.n = n_dst;
+    out.mc = multicast;
+    for (int q = 0; q < GORT_LUT_MAX_DST; q++) out.dst[q] = q < n_dst ? dst[q] : NULL;
     if (method == GORT_LUT_Q08) {
         lut_q08_kernel<<<n_sets, LUT_THREADS, 0, s>>>(n_sets, structure, lut);
         ctx->launches++;
+        if (n_dst > 0) {
+            lut_rows_out_kernel<<<ctx->sm_count * 4, 256, 0, s>>>((size_t) n_sets * GORT_LUT_STRIDE, out);
+            ctx->launches++;
+        }
         return check_cuda(ctx, cudaGetLastError(), "gort_lut launch");
     }
     // group cap: the geometry is shared by the whole group; with the flat kernels the grid no longer depends on the
@@ -967,11 +1021,11 @@ int launch_lut(gort_ctx *ctx, cudaStream_t s, int n_sets, const double *structur
         lut_prep_kernel<<<(unsigned) (((long) n * LUT_ZW + 127) / 128), 128, 0, s>>>(n, m0, structure, N, w);
         lut_vg_kernel<<<(unsigned) (((long) n * LUT_ZW + LUT_VG_THREADS - 1) / LUT_VG_THREADS), LUT_VG_THREADS, 0, s>>>(n, m0, structure, N, w);
         lut_tube_kernel<<<dim3((unsigned) n, 3), 32 * LUT_NSP, 0, s>>>(n, m0, structure, N, w);
-        lut_crown_kernel<1><<<dim3((unsigned) n, 3), 32 * LUT_NSP, sizeof(CrownSmem<1>), s>>>(n, m0, structure, N, w, lut);
-        lut_crown_kernel<LUT_SUB><<<dim3((unsigned) n, 3), 32 * LUT_NSP, sizeof(CrownSmem<LUT_SUB>), s>>>(n, m0, structure, N, w, lut);
+        lut_crown_kernel<1><<<dim3((unsigned) n, 3), 32 * LUT_NSP, sizeof(CrownSmem<1>), s>>>(n, m0, structure, N, w, out);
+        lut_crown_kernel<LUT_SUB><<<dim3((unsigned) n, 3), 32 * LUT_NSP, sizeof(CrownSmem<LUT_SUB>), s>>>(n, m0, structure, N, w, out);
         ctx->launches += 6;
     }
-    kopen_kernel<<<(unsigned) (((long) n_sets * 32 + 127) / 128), 128, 0, s>>>(n_sets, lut);
+    kopen_kernel<<<(unsigned) (((long) n_sets * 32 + 127) / 128), 128, 0, s>>>(n_sets, out);
     ctx->launches++;
     return check_cuda(ctx, cudaGetLastError(), "gort_lut launch");
 }

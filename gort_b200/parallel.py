@@ -131,6 +131,61 @@ def lut_generate_pipelined(structure, gort, rank, world, device, n_sub=4, method
     return out, d_blocks
 
 
+class PeerLutTable:
+    """A [rows][184] LUT table that exists on every rank of the group, with every rank's copy mapped into every
+    process (torch symmetric memory: cuMem allocations whose handles are exchanged once, NVLink P2P), plus the NVSwitch
+    multicast address of the table when the fabric offers one.  Plumbing only: the kernels that store into the peers'
+    copies are the library's own (gort_lut_batch_scatter_dev)."""
+
+    def __init__(self, rows, device, group=None):
+        import torch.distributed._symmetric_memory as symm
+        self.rows = rows
+        self.group = group if group is not None else dist.group.WORLD
+        self.table = symm.empty((rows, LUT_STRIDE), dtype=torch.float64, device=device)
+        self.handle = symm.rendezvous(self.table, self.group)
+        self.rank, self.world = self.handle.rank, self.handle.world_size
+        self.ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        try:
+            self.multicast_ptr = int(self.handle.multicast_ptr or 0)
+        except Exception:
+            self.multicast_ptr = 0
+
+    def peer_addresses(self, row):
+        """Addresses of `row` inside the other ranks' tables."""
+        off = row * LUT_STRIDE * 8
+        return [p + off for r, p in enumerate(self.ptrs) if r != self.rank]
+
+    def multicast_address(self, row):
+        return self.multicast_ptr + row * LUT_STRIDE * 8 if self.multicast_ptr else 0
+
+    def barrier(self):
+        """Device-side barrier of the group on the current stream (signal pads in symmetric memory)."""
+        self.handle.barrier()
+
+
+def lut_generate_peer(d_block, table, gort, stream, method=0, multicast=False, lo=None):
+    """This rank's block of LUT records computed into `table` on EVERY rank, no collective: the kernels that produce a
+    row also store it into the peers' tables (or once to the multicast address).  d_block: [6][m] device tensor, the
+    rank's contiguous block shard_range(table.rows, rank, world) (or starting at `lo`).  Everything -- a barrier of the
+    ranks (nobody still reads the old table), the kernels, a second barrier (all rows have landed everywhere) -- is
+    enqueued on `stream`, a torch.cuda.Stream other than the default one (the library maps a null stream to the
+    context's own, which the barriers would not be ordered with)."""
+    assert stream.cuda_stream != 0, "lut_generate_peer needs an explicit (non-default) stream"
+    if lo is None:
+        lo = shard_range(table.rows, table.rank, table.world)[0]
+    m = d_block.shape[1]
+    if multicast:
+        assert table.multicast_ptr, "no multicast address for this table"
+        dst = [table.multicast_address(lo)]
+    else:
+        dst = table.peer_addresses(lo)
+    with torch.cuda.stream(stream):
+        table.barrier()
+        gort.lut_scatter_dev(d_block, table.table[lo:lo + m], dst, method, multicast=multicast, stream=stream.cuda_stream)
+        table.barrier()
+    return table.table
+
+
 def write_lut_directory(luts, out_dir, names=None):
     """Rank 0: one "-W"-layout text file per parameter set (gortt.c:123-128), readable by `gortt -P`."""
     out_dir = Path(out_dir)

@@ -126,6 +126,20 @@ long gort_launch_count(const gort_ctx *ctx);
 int gort_lut_batch(gort_ctx *ctx, int n_sets, const double *structure, int method, double *lut);
 int gort_lut_batch_dev(gort_ctx *ctx, void *stream, int n_sets, const double *structure,
                        int method, double *lut);
+/* The same records, and copies of them stored by the producing kernels into further tables: the multi-GPU assembly of a
+ * LUT grid (BASELINE config 5) without a collective after the kernels.  Every rank owns a block of parameter sets and
+ * holds a full table; `lut` is this rank's block inside its own table, dst[0..n_dst) (a HOST array of device
+ * addresses, n_dst <= GORT_LUT_MAX_DST) are the addresses of the same block inside the other ranks' tables, mapped into
+ * this process (CUDA peer / symmetric memory over NVLink), or -- multicast != 0 -- NVSwitch multicast addresses of it,
+ * each written once and delivered to every GPU bound to the multicast object.  The stores are ordinary posted writes
+ * issued by the kernels that produce the rows (they run underneath the arithmetic of the other CTAs); they are
+ * complete when the work enqueued by this call is.  The caller synchronises the ranks around the call (nobody may
+ * still read the old contents; everybody must have finished before the table is read) -- gort_b200/parallel.py does
+ * it with the symmetric-memory barrier.  No reference counterpart (the reference computes one record per process,
+ * gortt.c:108-120). */
+#define GORT_LUT_MAX_DST 16
+int gort_lut_batch_scatter_dev(gort_ctx *ctx, void *stream, int n_sets, const double *structure, int method,
+                               double *lut, int n_dst, double *const *dst, int multicast);
 
 /* ---- the intermediates of gortt_gap_probabilities that never reach the BRDF or albedo path:
  *      gortt_calc_vb / gortt_calc_fb / gortt_calc_t_open (gortt_pn_kopen.c:925-1078) and the dk_open / k_open[h] rows of

@@ -95,3 +95,20 @@ def test_lut_allgather_shard_invariance(world, n_sets):
         assert luts.shape == (n_sets, 184)
         assert np.array_equal(luts, serial), "rank %d assembled different bits" % rank
         assert np.array_equal(gathered[:, 0], np.arange(n_sets, dtype=np.float64))
+
+
+def test_peer_table_addresses_skip_the_own_rank_and_step_by_whole_records():
+    """Address arithmetic of PeerLutTable (the symmetric allocation itself needs GPUs; bench.py / tools/dev_lut_peer.py
+    check the stores under torchrun)."""
+    from gort_b200.parallel import PeerLutTable
+    from gort_b200.api import LUT_STRIDE
+    t = PeerLutTable.__new__(PeerLutTable)
+    t.rank, t.world, t.rows = 2, 4, 1000
+    t.ptrs = [0x1000000, 0x2000000, 0x3000000, 0x4000000]
+    t.multicast_ptr = 0x9000000
+    lo = shard_range(t.rows, t.rank, t.world)[0]
+    want = [p + lo * LUT_STRIDE * 8 for r, p in enumerate(t.ptrs) if r != 2]
+    assert t.peer_addresses(lo) == want and len(want) == 3
+    assert t.multicast_address(lo) == 0x9000000 + lo * 184 * 8
+    t.multicast_ptr = 0
+    assert t.multicast_address(lo) == 0
