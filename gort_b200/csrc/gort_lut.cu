@@ -113,15 +113,23 @@ __device__ __forceinline__ double sqrt_lite(double x)
     const double y1 = fma(fma(e, 0.375, 0.5), y * e, y);
     return x == 0.0 ? 0.0 : x * y1;
 }
-// the same with the reference's clamp (gortt_pn_kopen.c:867: |a3| < 1e-10 -> 0) folded into the final select
+// the same with the reference's clamp (gortt_pn_kopen.c:867: |a3| < 1e-10 -> 0) folded into the final select.  The
+// comparison is made on the bit pattern (|x| < 1e-10 exactly, NaN compares false as in the reference): integer ALU
+// instead of one more instruction on the FP64 pipe, which is what bounds lut_tube_kernel.
 __device__ __forceinline__ double sqrt_clamped(double x)
 {
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
     const double e = fma(x, -(y * y), 1.0);
     const double y1 = fma(fma(e, 0.375, 0.5), y * e, y);
-    return fabs(x) < 0.0000000001 ? 0.0 : x * y1;
+    const unsigned hi = (unsigned) __double2hiint(x) & 0x7fffffffu, lo = (unsigned) __double2loint(x);
+    const bool tiny = hi < 0x3DDB7CDFu || (hi == 0x3DDB7CDFu && lo < 0xD9D7BDBBu);       // |x| < 1e-10 = 0x3DDB7CDFD9D7BDBB
+    return tiny ? 0.0 : x * y1;
 }
+
+__constant__ double c_simpson_index[2 * LUT_NOINT] = {
+    0.0, 1.0, 2.0, 3.0, 4.0, 5.0, 6.0, 7.0, 8.0, 9.0, 10.0, 11.0, 12.0, 13.0, 14.0, 15.0, 16.0, 17.0, 18.0, 19.0,
+    20.0, 21.0, 22.0, 23.0, 24.0, 25.0, 26.0, 27.0, 28.0, 29.0, 30.0, 31.0, 32.0, 33.0, 34.0, 35.0, 36.0, 37.0, 38.0, 39.0};
 
 // gortt_pn_kopen.c:858-872, as the reference writes it (used for the two end points)
 __device__ __forceinline__ double triang_fcn(double x, double b, double r, double tan_the)
@@ -147,16 +155,20 @@ __device__ __noinline__ double triang(double b, double r, double sint, double co
     const int m = LUT_NOINT;
     double h = .50 * (x0 - b) / (double) (float) m;
     const double c0 = r * r - b * b, c1 = -2.0 * b * h, c2 = -(1.0 + tant * tant) * (h * h), d = 2.0 * tant * h;
-    double sum1 = 0.0, sum2 = 0.0, f = 1.0;
+    // f(x_i) = (d i) sqrt(a3(i)): the factor d is taken out of the two sums (one FMA per point instead of two
+    // multiplications and an addition) and the sample indices come from a constant table instead of a running FP64 sum.
+    double sum1 = 0.0, sum2 = 0.0;
 #pragma unroll 2
-    for (int i = 0; i < m - 1; i++, f += 2.0) {
-        sum1 += (d * f) * sqrt_clamped(fma(fma(c2, f, c1), f, c0));      // odd points 1, 3, .., 37
-        const double g = f + 1.0;
-        sum2 += (d * g) * sqrt_clamped(fma(fma(c2, g, c1), g, c0));      // even points 2, 4, .., 38
+    for (int i = 0; i < m - 1; i++) {
+        const double f = c_simpson_index[2 * i + 1], g = c_simpson_index[2 * i + 2];
+        sum1 = fma(f, sqrt_clamped(fma(fma(c2, f, c1), f, c0)), sum1);   // odd points 1, 3, .., 37
+        sum2 = fma(g, sqrt_clamped(fma(fma(c2, g, c1), g, c0)), sum2);   // even points 2, 4, .., 38
     }
-    sum1 += (d * f) * sqrt_clamped(fma(fma(c2, f, c1), f, c0));          // point 39
-    double volume = 4.0 * sum1;
-    volume += 2.0 * sum2;
+    {
+        const double f = c_simpson_index[2 * m - 1];
+        sum1 = fma(f, sqrt_clamped(fma(fma(c2, f, c1), f, c0)), sum1);   // point 39
+    }
+    double volume = d * fma(4.0, sum1, 2.0 * sum2);
     volume += triang_fcn(x0, b, r, tant);
     volume += triang_fcn(b, b, r, tant);
     volume *= h / 3.0;
@@ -382,7 +394,17 @@ struct LutWork {
     double *es_all;     // [n][15][LUT_ZW]   E[S] towards every layer (only the intermediates path, launch_lut_dead)
     double *shp;        // [n][LUT_SHP]      derived crown-shape scalars and the 15 layer heights (seven FP64 divisions per
                         //                   set, done once by lut_plan_kernel instead of by every thread of every kernel)
+    // Compact work lists of the pass (lut_plan_kernel; order arbitrary, results do not depend on it), so that the heavy
+    // kernels run as persistent CTAs over exactly the items that exist instead of launching one (mostly empty) CTA per
+    // set: the C5 grid has one group head per 64 sets and one sub-group head per 8.
+    int *hl;            // [n]      group heads
+    int *s1;            // [n]      heads of single-member sub-groups
+    int *s8;            // [n]      heads of sub-groups of 2 .. LUT_SUB members
+    int *cnt;           // [LUT_NCNT]  lengths of hl, s1, s8; then the tickets of the persistent kernels (tube, crown<1>,
+                        //             crown<LUT_SUB>): items are handed out in order of request, not by a fixed stride --
+                        //             their durations differ (tube length, table size) and a fixed stride left a 10 % tail
 };
+#define LUT_NCNT 8
 #define LUT_SHP 32
 
 __device__ __forceinline__ bool same_shape(const double* __restrict__ st, size_t n, int a, int b)
@@ -437,30 +459,58 @@ __device__ __forceinline__ double layer_height_p(const LutWork& w, int i, int la
     return w.shp[(size_t) i * LUT_SHP + SHP_HP + layer];
 }
 
-// Groups and sub-groups.  m0 + i is the global index of set i of this pass: group boundaries sit at multiples of
-// group_cap of the GLOBAL index (and at the start of a pass), so the partition does not depend on the pass size.
-__global__ void __launch_bounds__(128)
-lut_plan_kernel(int n, int m0, int group_cap, const double* __restrict__ structure, size_t N, LutWork w)
+// Groups and sub-groups, for every pass of a call at once (one launch: the kernel is a serial walk per thread, and one
+// launch per 16 384 sets cost 8 x 46 us on the C5 grid).  Set e of the call belongs to pass e / chunk and has index
+// i = e % chunk inside it; m0 + e is its global index.  Group boundaries sit at multiples of group_cap of the GLOBAL
+// index and at pass boundaries (chunk is a multiple of group_cap), so the partition does not depend on the pass size.
+// head[] holds pass-local indices; the work lists and their counters are per pass (w.cnt[4 * pass + ..]).
+// One atomic per warp and pass instead of one per set: the lanes that append to the same pass's list are counted by a
+// ballot, the first of them reserves the slots.  (With every set a group head, 10^5 atomics on one address cost ~1 ms.)
+__device__ __forceinline__ void list_append(bool mine, int pass, int* cnt, int* list, int value)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int m = m0 + i;
+    const unsigned active = __activemask();
+    const unsigned same = __match_any_sync(active, pass);          // a warp straddles at most two passes
+    const unsigned who = __ballot_sync(active, mine) & same;
+    if (!mine) return;
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(who) - 1;
+    int slot = 0;
+    if (lane == leader) slot = atomicAdd(cnt, __popc(who));
+    slot = __shfl_sync(who, slot, leader);
+    list[slot + __popc(who & ((1u << lane) - 1u))] = value;
+}
+
+__global__ void __launch_bounds__(128)
+lut_plan_kernel(int n, int m0, int chunk, int group_cap, const double* __restrict__ structure, size_t N, LutWork w)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const int c = e / chunk, base = c * chunk;
+    const int i = e - base;
+    const int n_pass = min(chunk, n - base);
+    const int mb = m0 + base;                          // global index of the pass's first set
+    const int m = mb + i;
     // group head: walk back while the predecessor has the same shape and no boundary is crossed
     int h = i;
-    while (h > 0 && ((m0 + h) % group_cap) != 0 && same_shape(structure, N, m0 + h, m0 + h - 1)) h--;
-    w.head[i] = h;
+    while (h > 0 && ((mb + h) % group_cap) != 0 && same_shape(structure, N, mb + h, mb + h - 1)) h--;
+    w.head[e] = h;
     // sub-groups: the run of equal stem density that contains m, inside the group, cut every LUT_SUB members
     const double lambda = structure[0 * N + m];
     int rs = i;
-    while (rs > h && structure[0 * N + m0 + rs - 1] == lambda) rs--;
+    while (rs > h && structure[0 * N + mb + rs - 1] == lambda) rs--;
     int nj = 0;
     if ((i - rs) % LUT_SUB == 0) {
         nj = 1;
-        while (nj < LUT_SUB && i + nj < n && ((m0 + i + nj) % group_cap) != 0 &&
-               same_shape(structure, N, m0 + i + nj, m0 + i + nj - 1) && structure[0 * N + m0 + i + nj] == lambda) nj++;
+        while (nj < LUT_SUB && i + nj < n_pass && ((mb + i + nj) % group_cap) != 0 &&
+               same_shape(structure, N, mb + i + nj, mb + i + nj - 1) && structure[0 * N + mb + i + nj] == lambda) nj++;
     }
-    w.sub[i] = nj;
-    shape_store(w.shp + (size_t) i * LUT_SHP, shape_compute(structure, N, m));
+    w.sub[e] = nj;
+    shape_store(w.shp + (size_t) e * LUT_SHP, shape_compute(structure, N, m));
+    if (w.cnt) {
+        list_append(h == i, c, w.cnt + LUT_NCNT * c + 0, w.hl + base, i);
+        list_append(nj == 1, c, w.cnt + LUT_NCNT * c + 1, w.s1 + base, i);
+        list_append(nj > 1, c, w.cnt + LUT_NCNT * c + 2, w.s8 + base, i);
+    }
 }
 
 // theta' and its trig, E[S]: one thread per (group head, zenith)
@@ -535,23 +585,36 @@ lut_vg_kernel(int n, int m0, const double* __restrict__ structure, size_t N, Lut
     }
 }
 
-// Tube-volume difference per entry height, gortt_pn_kopen.c:496.  CTA = (group head, zenith third), warp = entry height.
-__global__ void __launch_bounds__(32 * LUT_NSP, 3)
-lut_tube_kernel(int n, int m0, const double* __restrict__ structure, size_t N, LutWork w)
+// Tube-volume difference per entry height, gortt_pn_kopen.c:496.  Item = (group head, zenith third, entry height) = one
+// warp's work; the warps share nothing, so they run as persistent warps (four to a CTA, ten CTAs per SM) striding over
+// the items of the head list.  (A 13-warp CTA per (set, third) held its registers until its slowest entry height was
+// done -- ncu: 43 % of the warp slots busy against 61 % allowed by the registers -- and launched 3 CTAs per set whether
+// or not the set was a group head.)
+#define LUT_TUBE_WARPS 4
+#define LUT_TUBE_OCC 10
+__global__ void __launch_bounds__(32 * LUT_TUBE_WARPS, LUT_TUBE_OCC)
+lut_tube_kernel(LutWork w)
 {
-    const int i = blockIdx.x;
-    if (w.head[i] != i) return;
-    const int lane = threadIdx.x & 31, k = threadIdx.x >> 5;
-    const int t = blockIdx.y * 32 + lane;
-    if (t >= GORT_NTH - 1) return;                                               // epgap only for t < nth - 1, :1099
-    const Shape S = shape_load(w, i);
-    const Ang a = ang_load(w, i, t);
-    const double hp0 = layer_height_p(w, i, 0);
-    const double hps = layer_height_p(w, i, GORT_NLAYERS - 2 - k);                  // :457, sp_i = 13 down to 1
-    w.tube[((size_t) i * LUT_NSP + k) * LUT_ZW + t] = tube_vol(S.c, a, hp0, hps, S.c.h2_p) - tube_vol(S.c, a, hp0, hps, S.c.h1_p);
+    const int lane = threadIdx.x & 31;
+    const int n_items = w.cnt[0] * (3 * LUT_NSP);
+    for (;;) {
+        int item = 0;
+        if (lane == 0) item = atomicAdd(&w.cnt[3], 1);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= n_items) break;
+        const int hi = item / (3 * LUT_NSP), wid = item - hi * (3 * LUT_NSP);
+        const int i = w.hl[hi];
+        const int third = wid / LUT_NSP, k = wid - third * LUT_NSP;
+        const int t = third * 32 + lane;
+        if (t >= GORT_NTH - 1) continue;                                         // epgap only for t < nth - 1, :1099
+        const Shape S = shape_load(w, i);
+        const Ang a = ang_load(w, i, t);
+        const double hp0 = layer_height_p(w, i, 0);
+        const double hps = layer_height_p(w, i, GORT_NLAYERS - 2 - k);              // :457, sp_i = 13 down to 1
+        w.tube[((size_t) i * LUT_NSP + k) * LUT_ZW + t] = tube_vol(S.c, a, hp0, hps, S.c.h2_p) - tube_vol(S.c, a, hp0, hps, S.c.h1_p);
+    }
 }
 
-// Crown-count loop and within-crown gap sums.  CTA = (sub-group head, zenith third), warp = entry height.
 // Where finished LUT rows go.  `local` is this GPU's copy (kopen_kernel reads the rows back from it); `dst` are further
 // copies of the same rows -- tables in the memory of peer GPUs mapped into this process (NVLink P2P), or one NVSwitch
 // multicast address that reaches every GPU of the group (`mc`: the store is then a multimem.st).  The rows leave with the
@@ -573,27 +636,41 @@ __device__ __forceinline__ void lut_store(const LutOut& o, size_t off, double v)
     }
 }
 
+// Crown-count loop and within-crown gap sums.  Item = (sub-group head, zenith third) = one CTA's work, warp = entry
+// height; persistent CTAs stride over the items of the sub-group list of their kind (SUB = 1: single-member sub-groups,
+// SUB = LUT_SUB: the others).
 template <int SUB>
 struct CrownSmem {
-    double tab[SUB][LUT_TAB];                // exp(-s_bin tau') per member
+    double tab[LUT_TAB][SUB];                // exp(-s_bin tau') per (bin, member): a bin's members are one 64-byte row,
+                                             // read with four 16-byte loads instead of eight 8-byte ones
     double part[LUT_NSP][SUB][32];           // partial within-crown gap sums per entry height
 };
+#define LUT_CROWN_OCC(SUB) ((SUB) == 1 ? 3 : 2)
 
 template <int SUB>
-__global__ void __launch_bounds__(32 * LUT_NSP, SUB == 1 ? 3 : 2)
-lut_crown_kernel(int n, int m0, const double* __restrict__ structure, size_t N, LutWork w, const LutOut out)
+__global__ void __launch_bounds__(32 * LUT_NSP, LUT_CROWN_OCC(SUB))
+lut_crown_kernel(int m0, const double* __restrict__ structure, size_t N, LutWork w, const LutOut out)
 {
     extern __shared__ __align__(16) unsigned char crown_smem_raw[];
     CrownSmem<SUB>& sm = *reinterpret_cast<CrownSmem<SUB>*>(crown_smem_raw);
-    double (*s_tab)[LUT_TAB] = sm.tab;
+    double (*s_tab)[SUB] = sm.tab;
     double (*s_part)[SUB][32] = sm.part;
-    const int i = blockIdx.x;
-    const int nj = w.sub[i];
-    // two instantiations share the sub-groups: SUB = 1 takes the single-member ones, SUB = LUT_SUB the others
-    if (nj == 0 || (SUB == 1) != (nj == 1)) return;
-    const int hd = w.head[i];
     const int lane = threadIdx.x & 31, k = threadIdx.x >> 5;
-    const int t = blockIdx.y * 32 + lane;
+    const int* __restrict__ list = SUB == 1 ? w.s1 : w.s8;
+    const int n_items = 3 * w.cnt[SUB == 1 ? 1 : 2];
+    // Shared memory across items: the table of item n+1 is written while slow warps may still read the partial sums of
+    // item n (another array); they have all left item n's crown-count loop (the barrier before the partial sums), and
+    // nobody enters item n+1's loop before the barrier after its table.
+  __shared__ int s_item;
+  for (;;) {
+    if (threadIdx.x == 0) s_item = atomicAdd(&w.cnt[SUB == 1 ? 4 : 5], 1);
+    __syncthreads();                                    // also: everybody has left the previous item's partial sums
+    const int item = s_item;
+    if (item >= n_items) break;
+    const int i = list[item / 3];
+    const int nj = w.sub[i];
+    const int hd = w.head[i];
+    const int t = (item % 3) * 32 + lane;
     const int m = m0 + i;
     const Shape S = shape_load(w, i);
     const double lambda = structure[0 * N + m];
@@ -607,7 +684,7 @@ lut_crown_kernel(int n, int m0, const double* __restrict__ structure, size_t N, 
         const int j = e / n_tab, bin = e - j * n_tab;
         const double favd_p = structure[5 * N + m + j] * S.ellip;
         const double sbin = (double) bin * S.c.ds;
-        s_tab[j][bin] = exp(-sbin * (0.5 * favd_p));
+        s_tab[bin][j] = exp(-sbin * (0.5 * favd_p));
     }
     const bool live = t < GORT_NTH, path = t < GORT_NTH - 1;
     double e_t[SUB];
@@ -638,8 +715,8 @@ lut_crown_kernel(int n, int m0, const double* __restrict__ structure, size_t N, 
         // Hot loop without branches: the bin comes from the fast form; a crown count whose fast form lands within 1e-9
         // of a bin boundary, or whose bin lies beyond the table, only raises a flag (and reads a clamped table row).
         // A flagged (zenith, entry height) -- about one in 10^6 -- is then redone from scratch with the literal formulas.
-        double pw = c0, qn = 1.0;
-        bool redo = false;
+        double pw = c0, qn = 1.0, u_last = 0.0;
+        bool redo = !(q >= 0.0 && q <= 1.0 && spd > 0.0);
 #pragma unroll 5
         for (int nn = 1; nn <= LUT_MAXCROWNS; nn++) {                            // :489
             pw *= temp1;                                                         // temp1^n e^-t / (1 - e^-t) P(s')
@@ -652,15 +729,29 @@ lut_crown_kernel(int n, int m0, const double* __restrict__ structure, size_t N, 
             // units of 2^-30 = 9.3e-10, below.  A fraction within 2 units of either end (|u - rint(u)| < 1.9e-9, a
             // superset of the 1e-9 rule), a sum that left the binade (u >= 2^22, NaN) or a bin beyond the table raise
             // the flag.
+            // With 0 <= q <= 1 and s'/ds > 0 the u of successive crown counts never decrease (q^n does not increase, the
+            // FMA is monotonic), so the range tests -- u left the binade, or the bin lies beyond the table -- are made once,
+            // on the last u, after the loop; inside it only the fraction is tested and the table row clamped.
             const long long ub = __double_as_longlong(u + 4194304.0);
             const int idx = (int) ((ub >> 30) & 0x3fffff);
-            const int frac = (int) (ub & 0x3fffffff);
-            redo |= (frac < 2) | (frac > 0x3fffffff - 2) | ((ub >> 52) != 0x415) | (idx >= n_tab);
+            const unsigned frac = (unsigned) ub & 0x3fffffffu;
+            redo |= (frac - 2u) > (0x3fffffffu - 4u);
+            u_last = u;
             const int row = min(idx, n_tab - 1);
             // gortt_calc_epgap + gortt_calc_pgap, :1110-1114, :1138
+            if (SUB == 1) {
+                e_t[0] = fma(s_tab[row][0], wgt, e_t[0]);
+            } else {
+                const double2* __restrict__ tp = reinterpret_cast<const double2*>(&s_tab[row][0]);
 #pragma unroll
-            for (int j = 0; j < SUB; j++) e_t[j] = fma(s_tab[j][row], wgt, e_t[j]);
+                for (int j2 = 0; j2 < SUB / 2; j2++) {
+                    const double2 v = tp[j2];
+                    e_t[2 * j2] = fma(v.x, wgt, e_t[2 * j2]);
+                    e_t[2 * j2 + 1] = fma(v.y, wgt, e_t[2 * j2 + 1]);
+                }
+            }
         }
+        redo |= !(u_last >= 0.0 && u_last < (double) (n_tab - 1));
         if (redo) {
 #pragma unroll
             for (int j = 0; j < SUB; j++) e_t[j] = 0.0;
@@ -676,7 +767,7 @@ lut_crown_kernel(int n, int m0, const double* __restrict__ structure, size_t N, 
                 const int idx = (int) u;
                 if (idx >= 0 && idx < n_tab) {
 #pragma unroll
-                    for (int j = 0; j < SUB; j++) e_t[j] = fma(s_tab[j][idx], wgt, e_t[j]);
+                    for (int j = 0; j < SUB; j++) e_t[j] = fma(s_tab[idx][j], wgt, e_t[j]);
                 } else {
                     const double sbin = (double) idx * S.c.ds;
 #pragma unroll
@@ -702,6 +793,7 @@ lut_crown_kernel(int n, int m0, const double* __restrict__ structure, size_t N, 
             lut_store(out, (size_t) (m + j) * GORT_LUT_STRIDE + GORT_NTH + t, e);
         }
     }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -955,11 +1047,12 @@ int launch_lut_dead(gort_ctx *ctx, cudaStream_t s, int n_sets, const double *str
     w.shp = w.es_all + (size_t) chunk * GORT_NLAYERS * LUT_ZW;
     w.head = (int *) (w.shp + (size_t) chunk * LUT_SHP);
     w.sub = w.head + chunk;
+    w.hl = w.s1 = w.s8 = w.cnt = NULL;                   // no work lists on this path: its kernels walk the sets
     const size_t N = (size_t) n_sets;
     for (int m0 = 0; m0 < n_sets; m0 += chunk) {
         const int n = n_sets - m0 < chunk ? n_sets - m0 : chunk;
         DeadOut o = {vb, fb, t_open, dt_open, dk_open, k_open};
-        lut_plan_kernel<<<(n + 127) / 128, 128, 0, s>>>(n, m0, cap, structure, N, w);
+        lut_plan_kernel<<<(n + 127) / 128, 128, 0, s>>>(n, m0, n, cap, structure, N, w);
         lut_prep_kernel<<<(unsigned) (((long) n * LUT_ZW + 127) / 128), 128, 0, s>>>(n, m0, structure, N, w);
         lut_vg_kernel<<<(unsigned) (((long) n * LUT_ZW + LUT_VG_THREADS - 1) / LUT_VG_THREADS), LUT_VG_THREADS, 0, s>>>(n, m0, structure, N, w);
         lut_es_all_kernel<<<(unsigned) (((long) n * LUT_ZW * GORT_NLAYERS + 127) / 128), 128, 0, s>>>(n, m0, structure, N, w);
@@ -1002,9 +1095,11 @@ int launch_lut_out(gort_ctx *ctx, cudaStream_t s, int n_sets, const double *stru
         ctx->lut_attr_set = 1;
     }
     const int chunk = n_sets < LUT_CHUNK ? n_sets : LUT_CHUNK;
-    // workspace of one pass
-    const size_t per_set = sizeof(double) * ((4 + GORT_NLAYERS + LUT_NSP) * LUT_ZW + LUT_SHP) + 2 * sizeof(int);
-    char *base = (char *) workspace(ctx, per_set * (size_t) chunk + 256);
+    const int n_pass = (n_sets + chunk - 1) / chunk;
+    // workspace: per-zenith arrays for one pass, the plan (shapes, heads, sub-groups, work lists) for the whole call
+    const size_t per_set_pass = sizeof(double) * ((4 + GORT_NLAYERS + LUT_NSP) * LUT_ZW);
+    const size_t per_set_plan = sizeof(double) * LUT_SHP + 5 * sizeof(int);
+    char *base = (char *) workspace(ctx, per_set_pass * (size_t) chunk + per_set_plan * (size_t) n_sets + sizeof(int) * LUT_NCNT * (size_t) n_pass + 256);
     if (!base) return GORT_ERR_NOMEM;
     LutWork w;
     w.trig = (double *) base;
@@ -1012,18 +1107,32 @@ int launch_lut_out(gort_ctx *ctx, cudaStream_t s, int n_sets, const double *stru
     w.tube = w.vg + (size_t) chunk * GORT_NLAYERS * LUT_ZW;
     w.es_all = NULL;
     w.shp = w.tube + (size_t) chunk * LUT_NSP * LUT_ZW;
-    w.head = (int *) (w.shp + (size_t) chunk * LUT_SHP);
-    w.sub = w.head + chunk;
+    w.head = (int *) (w.shp + (size_t) n_sets * LUT_SHP);
+    w.sub = w.head + n_sets;
+    w.hl = w.sub + n_sets;
+    w.s1 = w.hl + n_sets;
+    w.s8 = w.s1 + n_sets;
+    w.cnt = w.s8 + n_sets;
     const size_t N = (size_t) n_sets;
-    for (int m0 = 0; m0 < n_sets; m0 += chunk) {
+    cudaError_t me = cudaMemsetAsync(w.cnt, 0, sizeof(int) * LUT_NCNT * (size_t) n_pass, s);
+    if (me != cudaSuccess) return check_cuda(ctx, me, "gort_lut counters");
+    lut_plan_kernel<<<(n_sets + 127) / 128, 128, 0, s>>>(n_sets, 0, chunk, cap, structure, N, w);
+    ctx->launches++;
+    for (int m0 = 0, c = 0; m0 < n_sets; m0 += chunk, c++) {
         const int n = n_sets - m0 < chunk ? n_sets - m0 : chunk;
-        lut_plan_kernel<<<(n + 127) / 128, 128, 0, s>>>(n, m0, cap, structure, N, w);
-        lut_prep_kernel<<<(unsigned) (((long) n * LUT_ZW + 127) / 128), 128, 0, s>>>(n, m0, structure, N, w);
-        lut_vg_kernel<<<(unsigned) (((long) n * LUT_ZW + LUT_VG_THREADS - 1) / LUT_VG_THREADS), LUT_VG_THREADS, 0, s>>>(n, m0, structure, N, w);
-        lut_tube_kernel<<<dim3((unsigned) n, 3), 32 * LUT_NSP, 0, s>>>(n, m0, structure, N, w);
-        lut_crown_kernel<1><<<dim3((unsigned) n, 3), 32 * LUT_NSP, sizeof(CrownSmem<1>), s>>>(n, m0, structure, N, w, out);
-        lut_crown_kernel<LUT_SUB><<<dim3((unsigned) n, 3), 32 * LUT_NSP, sizeof(CrownSmem<LUT_SUB>), s>>>(n, m0, structure, N, w, out);
-        ctx->launches += 6;
+        LutWork wc = w;                                  // this pass's slice of the plan
+        wc.shp += (size_t) m0 * LUT_SHP; wc.head += m0; wc.sub += m0; wc.hl += m0; wc.s1 += m0; wc.s8 += m0; wc.cnt += LUT_NCNT * c;
+        LutOut oc = out;                                 // the crown kernels index rows by the global set index themselves
+        lut_prep_kernel<<<(unsigned) (((long) n * LUT_ZW + 127) / 128), 128, 0, s>>>(n, m0, structure, N, wc);
+        lut_vg_kernel<<<(unsigned) (((long) n * LUT_ZW + LUT_VG_THREADS - 1) / LUT_VG_THREADS), LUT_VG_THREADS, 0, s>>>(n, m0, structure, N, wc);
+        const long tube_ctas = ((long) n * 3 * LUT_NSP + LUT_TUBE_WARPS - 1) / LUT_TUBE_WARPS;
+        const long tube_max = (long) ctx->sm_count * LUT_TUBE_OCC;      // 6 .. 12 CTAs per SM measured the same
+        lut_tube_kernel<<<(unsigned) (tube_ctas < tube_max ? tube_ctas : tube_max), 32 * LUT_TUBE_WARPS, 0, s>>>(wc);
+        const long items = (long) n * 3;
+        const long c1 = (long) ctx->sm_count * LUT_CROWN_OCC(1), c8 = (long) ctx->sm_count * LUT_CROWN_OCC(LUT_SUB);
+        lut_crown_kernel<1><<<(unsigned) (items < c1 ? items : c1), 32 * LUT_NSP, sizeof(CrownSmem<1>), s>>>(m0, structure, N, wc, oc);
+        lut_crown_kernel<LUT_SUB><<<(unsigned) (items < c8 ? items : c8), 32 * LUT_NSP, sizeof(CrownSmem<LUT_SUB>), s>>>(m0, structure, N, wc, oc);
+        ctx->launches += 5;
     }
     kopen_kernel<<<(unsigned) (((long) n_sets * 32 + 127) / 128), 128, 0, s>>>(n_sets, out);
     ctx->launches++;
