@@ -548,22 +548,25 @@ __device__ __forceinline__ Ang ang_load(const LutWork& w, int i, int t)
 // the rounding of h - z, ~1e-16.)  One thread per (group head, zenith); its cross-sections sit in its own column of
 // shared memory (no barrier: nobody else reads them).
 #define LUT_VG_THREADS 128
-__global__ void __launch_bounds__(LUT_VG_THREADS, 6)
+__global__ void __launch_bounds__(LUT_VG_THREADS, 7)
 lut_vg_kernel(int n, int m0, const double* __restrict__ structure, size_t N, LutWork w)
 {
-    __shared__ double s_A[30][LUT_VG_THREADS];           // 14 + K <= 29 distinct cross-sections of this thread
-    __shared__ double s_zk[16][LUT_VG_THREADS];          // its crown-centre heights
+    // 14 + K <= 29 distinct cross-sections of this thread.  (The crown-centre heights used to sit in a second array; at
+    // 47 KB per CTA only 16 warps fitted an SM -- ncu: 21 % of the warp slots, FP64 pipe 37 %.  They are a running sum,
+    // :162, and are now simply formed again in the order they are needed.)
+    __shared__ double s_A[30][LUT_VG_THREADS];
     const long e = (long) blockIdx.x * blockDim.x + threadIdx.x;
     const int i = (int) (e / LUT_ZW), t = (int) (e - (long) i * LUT_ZW);
     if (i >= n || w.head[i] != i || t >= GORT_NTH) return;
     const Shape S = shape_load(w, i);
     const Ang a = ang_load(w, i, t);
     double* vg = w.vg + (size_t) i * GORT_NLAYERS * LUT_ZW + t;
-    // crown-centre heights of the midpoint rule, gortt_pn_kopen.c:162: a running sum
+    // number of crown-centre heights of the midpoint rule, gortt_pn_kopen.c:162: a running sum
+    const double z0 = S.c.h1_p + S.c.dz_p / 2.0;
     int K = 0;
     {
-        double z = S.c.h1_p + S.c.dz_p / 2.0;
-        for (; z <= S.c.h2_p && K < 16; z += S.c.dz_p) s_zk[K++][threadIdx.x] = z;
+        double z = z0;
+        for (; z <= S.c.h2_p && K < 16; z += S.c.dz_p) K++;
         if (K == 16 && z <= S.c.h2_p) K = 17;                    // more than 16 midpoints: the literal rule below
     }
     if (K < 1 || K >= 16) {
@@ -571,12 +574,16 @@ lut_vg_kernel(int n, int m0, const double* __restrict__ structure, size_t N, Lut
         for (int h = 0; h < GORT_NLAYERS; h++) vg[(size_t) h * LUT_ZW] = proj_volume(S.c, a, layer_height_p(w, i, h));
         return;
     }
-    // distinct cross-sections j = 0 .. 13 + K: (h, z) = (0, K-1-j) for j < K, (j-K+1, 0) after
+    // distinct cross-sections j = 0 .. 13 + K: (h, z) = (0, z_{K-1-j}) for j < K, (j-K+1, z_0) after
+    {
+        const double h0 = layer_height_p(w, i, 0);
+        double z = z0;
 #pragma unroll 1
-    for (int j = 0; j < GORT_NLAYERS + K - 1; j++) {
-        const int ih = max(0, j - (K - 1)), k = ih - (j - (K - 1));
-        s_A[j][threadIdx.x] = cross_section(S.c, a, layer_height_p(w, i, ih), s_zk[k][threadIdx.x]);
+        for (int k = 0; k < K; k++, z += S.c.dz_p) s_A[K - 1 - k][threadIdx.x] = cross_section(S.c, a, h0, z);
     }
+#pragma unroll 1
+    for (int j = K; j < GORT_NLAYERS + K - 1; j++)
+        s_A[j][threadIdx.x] = cross_section(S.c, a, layer_height_p(w, i, j - (K - 1)), z0);
 #pragma unroll 1
     for (int h = 0; h < GORT_NLAYERS; h++) {
         double vol = 0.0;
@@ -715,28 +722,29 @@ lut_crown_kernel(int m0, const double* __restrict__ structure, size_t N, LutWork
         // Hot loop without branches: the bin comes from the fast form; a crown count whose fast form lands within 1e-9
         // of a bin boundary, or whose bin lies beyond the table, only raises a flag (and reads a clamped table row).
         // A flagged (zenith, entry height) -- about one in 10^6 -- is then redone from scratch with the literal formulas.
-        double pw = c0, qn = 1.0, u_last = 0.0;
+        double pw = c0, qn = 1.0, ub_last = 4194304.0;
         bool redo = !(q >= 0.0 && q <= 1.0 && spd > 0.0);
-#pragma unroll 5
+        // floor(u) and the distance of u from the nearest integer without the conversion unit (FRND / F2I run at a
+        // quarter of the FP64 rate and made this loop XU-bound: ncu 36 % XU against 45 % FP64): 0.5 <= u < 2^22, so
+        // u + 2^22 has the exponent of 2^22, its mantissa holds floor(u) above bit 30 and the fraction of u, in units
+        // of 2^-30 = 9.3e-10, below.  The 2^22 is folded into the FMA's addend (one rounding to 2^-30 units instead of
+        // two; the addend's own rounding and the FMA's are at most one unit together).  A fraction within 2 units of
+        // either end (|u - rint(u)| < 1.9e-9, a superset of the 1e-9 rule plus that unit) raises the flag.
+        // With 0 <= q <= 1 and s'/ds > 0 the u of successive crown counts never decrease (q^n does not increase, the
+        // FMA is monotonic), so the range tests -- u left the binade, or the bin lies beyond the table -- are made
+        // once, on the last u, after the loop; inside it only the fraction is tested and the table row clamped.
+        const double spd5m = spd5 + 4194304.0;
+#pragma unroll
         for (int nn = 1; nn <= LUT_MAXCROWNS; nn++) {                            // :489
             pw *= temp1;                                                         // temp1^n e^-t / (1 - e^-t) P(s')
             qn *= q;
             const double wgt = pw * c_inv_fact[nn];
-            const double u = fma(-spd, qn, spd5);
-            // floor(u) and the distance of u from the nearest integer without the conversion unit (FRND / F2I run at a
-            // quarter of the FP64 rate and made this loop XU-bound: ncu 36 % XU against 45 % FP64): 0.5 <= u < 2^22, so
-            // u + 2^22 has the exponent of 2^22, its mantissa holds floor(u) above bit 30 and the fraction of u, in
-            // units of 2^-30 = 9.3e-10, below.  A fraction within 2 units of either end (|u - rint(u)| < 1.9e-9, a
-            // superset of the 1e-9 rule), a sum that left the binade (u >= 2^22, NaN) or a bin beyond the table raise
-            // the flag.
-            // With 0 <= q <= 1 and s'/ds > 0 the u of successive crown counts never decrease (q^n does not increase, the
-            // FMA is monotonic), so the range tests -- u left the binade, or the bin lies beyond the table -- are made once,
-            // on the last u, after the loop; inside it only the fraction is tested and the table row clamped.
-            const long long ub = __double_as_longlong(u + 4194304.0);
+            const double ubd = fma(-spd, qn, spd5m);
+            const long long ub = __double_as_longlong(ubd);
             const int idx = (int) ((ub >> 30) & 0x3fffff);
             const unsigned frac = (unsigned) ub & 0x3fffffffu;
             redo |= (frac - 2u) > (0x3fffffffu - 4u);
-            u_last = u;
+            ub_last = ubd;
             const int row = min(idx, n_tab - 1);
             // gortt_calc_epgap + gortt_calc_pgap, :1110-1114, :1138
             if (SUB == 1) {
@@ -751,6 +759,7 @@ lut_crown_kernel(int m0, const double* __restrict__ structure, size_t N, LutWork
                 }
             }
         }
+        const double u_last = ub_last - 4194304.0;
         redo |= !(u_last >= 0.0 && u_last < (double) (n_tab - 1));
         if (redo) {
 #pragma unroll
