@@ -384,7 +384,7 @@ def test_c5_full_grid_properties_and_group_invariance(gort, oracle):
     assert np.all(lut[ok, 182] >= 0) and np.all(lut[ok, 182] <= 1.01)      # trapezoid of p_n0 sin(2 theta) over the clamped theta grid
     # same bits alone, in a different batch composition, and across chunk boundaries
     rng = np.random.Generator(np.random.PCG64(5))
-    pick = np.unique(np.concatenate([rng.integers(0, M, 40), [0, 63, 64, 65, 127, 128, M - 1]]))
+    pick = np.unique(np.concatenate([rng.integers(0, M, 40), [0, 63, 64, 65, 127, 128, 16383, 16384, 16385, 7 * 16384 - 1, 7 * 16384, M - 1]]))   # group and pass boundaries
     for k in pick:
         alone = gort.lut(np.ascontiguousarray(st[:, k:k + 1]))[0]
         assert np.array_equal(alone, lut[k], equal_nan=True), "set %d differs when computed alone" % k
