@@ -725,6 +725,22 @@ def extras(g, torch, dev, ts, near_cpus=None):
                           "note": "same sweep, lines permuted: every line starts a new run, so the (sun, lambda) terms "
                                   "(2 divisions + ~35 FP64 operations per wavelength) are rebuilt per line instead of once per "
                                   "36 lines and the kernel turns FP64-bound; callers that can should keep lines sharing a sun adjacent"}
+    # back to back into ROTATING output buffers (a consumer that double-buffers): the output pointer is part of the
+    # call's signature, so overlap mode does not engage and every call pays its geometry kernel and start-up
+    d_r2 = E(1, G, Wp)
+    binds = [g.brdf_dev_bind(d_st, d_lut, d_ang, d_rl[0], d_tl[0], d_rs[0], o, stream=stream) for o in (d_r, d_r2)]
+    g.set_overlap(True)
+
+    def rotate(n=40):
+        for k in range(n):
+            binds[k & 1]()
+    rot_ms = _time_dev(torch, ts, rotate) / 40
+    g.set_overlap(False)
+    res["c2_rotated_outputs"] = {"calls": 40, "ms_per_call": rot_ms, "evals_per_s": G * W / (rot_ms * 1e-3),
+                                 "hbm_frac": 8.0 * G * W / (rot_ms * 1e-3) / 1e9 / hbm,
+                                 "note": "40 calls back to back alternating between two output buffers, overlap mode requested: "
+                                         "it applies only to repeated calls into the same buffers, so this is plain stream order"}
+    del d_r2, binds
     d_sc = E(1, G, Wp, 4)
     sc_ms = _time_dev(torch, ts, lambda: g.brdf_dev(d_st, d_lut, d_ang, d_rl[0], d_tl[0], d_rs[0], d_r, scomp=d_sc, stream=stream))
     res["c2_prnspec"] = {"lines": G, "wavelengths": W, "brdf_ms": sc_ms, "evals_per_s": G * W / (sc_ms * 1e-3),
