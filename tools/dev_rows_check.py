@@ -69,6 +69,11 @@ def run(tag):
             ts.synchronize()
             gm, rm, n = g.profile_end()
             res["us_geom_kernel"] = gm * 1e3; res["us_per_wavelength_kernel"] = rm * 1e3
+            g.kernel_stamps_enable(True)
+            for _ in range(10):
+                call(); ts.synchronize()
+            res["stamps"] = g.kernel_stamps()
+            g.kernel_stamps_enable(False)
             np.save(ROOT / "gpurun_out" / ("rows_check_%s.npy" % tag), h[0, ::97, :2101])
     g.synchronize()
     g.close()
