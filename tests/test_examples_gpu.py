@@ -30,3 +30,22 @@ def test_enkf_forward_example(gort, tmp_path):
     rl, tl, rs = gort.spectra(leaf, soil, wl)
     ref = gort.brdf(st, lut, ang, rl, tl, rs)
     assert np.array_equal(out, ref, equal_nan=True)
+
+
+def test_lut_grid_multigpu_example(gort, tmp_path):
+    """examples/lut_grid_multigpu.cu: one C++ host process, every visible GPU computing its block of a LUT grid and
+    storing it into every GPU's table (gort_lut_batch_scatter_dev over peer mappings; with one GPU the degenerate case).
+    The assembled table must hold the bits one GPU computes, on every GPU."""
+    exe = ROOT / "gort_b200" / "bin" / "lut_grid_multigpu"
+    assert exe.exists(), "build with `make -C gort_b200/csrc`"
+    st = np.ascontiguousarray(wk.c5_lut_grid((3, 3, 2, 3, 5, 7))["structure"])
+    M = st.shape[1]
+    src, dst = tmp_path / "structure.bin", tmp_path / "lut.bin"
+    with open(src, "wb") as f:
+        np.array([M], dtype=np.int32).tofile(f)
+        st.tofile(f)
+    p = subprocess.run([str(exe), str(src), str(dst)], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stdout + p.stderr
+    assert "tables identical: yes" in p.stdout
+    out = np.fromfile(dst, dtype=np.float64).reshape(M, -1)
+    assert np.array_equal(out, gort.lut(st), equal_nan=True)
