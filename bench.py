@@ -218,7 +218,7 @@ def sweep_inputs(rank):
 def _cpu_worker(args):
     kind, st, lut, ang, rl, tl, rs, reps = args
     import checkers
-    chk = checkers.ref() if kind == "reference" else checkers.oracle()
+    chk = checkers.ref() if kind == "reference" else checkers.ref_makefile_flags() if kind == "reference-g" else checkers.oracle()
     t0 = time.perf_counter()
     n = chk.brdf_repeat(st, lut, ang, rl, tl, rs, reps)
     return n, time.perf_counter() - t0
@@ -911,9 +911,18 @@ def cpu_baseline(gpu_rsurf=None, wavelength=None):
         n1, t1 = cpu_arm_step(pool, cores, kind, st, lut, ang, rl, tl, rs, lines)
         reps = int(min(40, max(1, 12.0 / max(t1, 1e-3))))
         n, t = cpu_arm_step(pool, cores, kind, st, lut, ang, rl, tl, rs, lines, reps=reps)
+        # the same sample through the build with the reference makefile's own flags (-g: no optimisation), SURVEY.md 8d
+        import checkers
+        slow = None
+        if kind == "reference" and checkers.ref_makefile_flags() is not None:
+            ng, tg = cpu_arm_step(pool, cores, "reference-g", st, lut, ang, rl, tl, rs, lines, reps=max(1, reps // 8))
+            slow = {"value": ng / tg, "unit": UNIT, "cores": cores, "flags": "-Wall -g (the reference makefile's CFLAGS)",
+                    "note": "same bits as the canonical -O2 -ffp-contract=off build (tests/test_oracle_cpu.py)"}
     out = {"value": n / t, "unit": UNIT, "cores": cores, "kind": kind,
            "sample": "%d lines x 2101 bands x %d reps per core (strided slice of the c2 sweep), in-process, "
                      "LUT and spectra given" % (lines, reps)}
+    if slow is not None:
+        out["makefile_flag_build"] = slow
     if parity is not None:
         out["parity"] = parity
     return out

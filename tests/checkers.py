@@ -208,6 +208,16 @@ def ref():
     return _cache["ref"]
 
 
+def ref_makefile_flags():
+    """the unmodified reference built with its own makefile's CFLAGS (-g, no optimisation): for timing only"""
+    if "ref_g" not in _cache:
+        so = ROOT / "oracle" / "_ref" / "libgortt_ref_g.so"
+        if not so.exists() and os.path.exists("/root/reference/gortt.c"):
+            build_checkers()
+        _cache["ref_g"] = Checker(C.CDLL(str(so)), "ref_") if so.exists() else None
+    return _cache["ref_g"]
+
+
 REF_BIN = ROOT / "oracle" / "_ref" / "gortt_ref"
 
 

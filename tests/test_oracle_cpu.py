@@ -12,6 +12,7 @@ from pathlib import Path
 import numpy as np
 import pytest
 
+import checkers
 from gort_b200 import workloads as wk
 
 GOLD = Path(__file__).resolve().parent / "golden" / "ref_vectors.npz"
@@ -129,6 +130,26 @@ def test_oracle_vs_live_reference_on_fresh_seeds(oracle, ref):
         assert all(same(a, b) for a, b in zip(bo, br))
     eo, er = oracle.energy(st[:, 0], lo, ang[:2], *so), ref.energy(st[:, 0], lo, ang[:2], *so)
     assert all(same(a, b) for a, b in zip(eo, er))
+
+
+def test_makefile_flag_build_of_the_reference_gives_the_same_bits(ref):
+    """oracle/_ref/libgortt_ref_g.so: the reference compiled with its own makefile's CFLAGS (-Wall -g).  bench.py times it
+    next to the canonical -O2 -ffp-contract=off build (SURVEY.md 8c / 8d say the two are bit-identical: checked here)."""
+    slow = checkers.ref_makefile_flags()
+    if slow is None:
+        pytest.skip("oracle/_ref/libgortt_ref_g.so not built (no /root/reference here)")
+    rng = np.random.Generator(np.random.PCG64(7))
+    st = wk.random_structures(rng, 2)
+    leaf = wk.random_leaves(rng, 2)
+    wl = np.sort(rng.uniform(400, 2500, 9))
+    ang = np.stack([rng.uniform(-85, 89, 20), rng.uniform(-720, 720, 20), rng.uniform(-85, 89, 20), rng.uniform(-720, 720, 20)], axis=1)
+    for m in range(2):
+        la, lb = ref.lut(st[:, m]), slow.lut(st[:, m])
+        assert same(la, lb)
+        sa, sb = ref.spectra(leaf[:, m], wk.DEFAULT_SOIL, wl), slow.spectra(leaf[:, m], wk.DEFAULT_SOIL, wl)
+        assert all(same(a, b) for a, b in zip(sa, sb))
+        assert all(same(a, b) for a, b in zip(ref.brdf(st[:, m], la, ang, *sa), slow.brdf(st[:, m], lb, ang, *sb)))
+    assert all(same(a, b) for a, b in zip(ref.energy(st[:, 0], la, ang[:2], *sa), slow.energy(st[:, 0], la, ang[:2], *sa)))
 
 
 def test_prospect_exponential_integral_matches_scipy(oracle):
