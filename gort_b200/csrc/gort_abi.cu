@@ -141,6 +141,7 @@ void gort_destroy(gort_ctx *ctx)
     if (ctx->d_soil) cudaFree(ctx->d_soil);
     if (ctx->prof_ev) { for (int i = 0; i < 3 * ctx->prof_cap; i++) cudaEventDestroy(ctx->prof_ev[i]); free(ctx->prof_ev); }
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); for (int i = 0; i < 6; i++) if (ctx->fwd_ev[i]) cudaEventDestroy(ctx->fwd_ev[i]); cudaStreamDestroy(ctx->copy_stream); }
+    if (ctx->copy_stream_out) { cudaStreamSynchronize(ctx->copy_stream_out); cudaStreamDestroy(ctx->copy_stream_out); }
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     free(ctx);
 }
@@ -592,9 +593,12 @@ int gort_forward_batch(gort_ctx *ctx, const gort_shape *shape, int lut_method, c
     TRYCUDA(ctx, cudaSetDevice(ctx->device), "cudaSetDevice");
     if (!ctx->copy_stream) {
         TRYCUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking), "cudaStreamCreate");
+        TRYCUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream_out, cudaStreamNonBlocking), "cudaStreamCreate");
         for (int i = 0; i < 6; i++) TRYCUDA(ctx, cudaEventCreateWithFlags(&ctx->fwd_ev[i], cudaEventDisableTiming), "cudaEventCreate");
     }
-    cudaStream_t A = ctx->stream, B = ctx->copy_stream;
+    // three streams: the two copy directions have their own engines, and on ONE copy stream the inputs of chunk i+1 would
+    // queue behind the results of chunk i, which wait for chunk i's kernels -- no copy would run under a kernel
+    cudaStream_t A = ctx->stream, B = ctx->copy_stream, D = ctx->copy_stream_out;
     // chunk: at least 8 per batch when the batch is large, never above 16384 members, at least 1024
     size_t C = (M + 7) / 8;
     if (C > 16384) C = 16384;
@@ -612,7 +616,7 @@ int gort_forward_batch(gort_ctx *ctx, const gort_shape *shape, int lut_method, c
             buf[b][k] = (double *) scratch(ctx, 9 * b + k, sz[k] * sizeof(double));
             if (!buf[b][k]) return GORT_ERR_NOMEM;
         }
-    // events per buffer: [b] inputs ready (B), [2+b] kernels done (A), [4+b] outputs copied (B)
+    // events per buffer: [b] inputs ready (B), [2+b] kernels done (A), [4+b] outputs copied (D)
     gort_shape sh = *shape;
     sh.spectra_per_set = 1;
     sh.out_pitch = 0;
@@ -637,12 +641,13 @@ int gort_forward_batch(gort_ctx *ctx, const gort_shape *shape, int lut_method, c
         TRY(launch_brdf(ctx, A, sh, buf[b][0], buf[b][4], per_set_geom ? buf[b][3] : d_ang_shared, buf[b][5], buf[b][6], buf[b][7],
                         buf[b][8], NULL, NULL));
         TRYCUDA(ctx, cudaEventRecord(ctx->fwd_ev[2 + b], A), "cudaEventRecord");
-        // -- stream B: results of this chunk --
-        TRYCUDA(ctx, cudaStreamWaitEvent(B, ctx->fwd_ev[2 + b], 0), "cudaStreamWaitEvent");
-        TRYCUDA(ctx, cudaMemcpyAsync(rsurf + m0 * G * W, buf[b][8], c * G * W * sizeof(double), cudaMemcpyDeviceToHost, B), "forward: rsurf");
-        if (lut_out) TRYCUDA(ctx, cudaMemcpyAsync(lut_out + m0 * GORT_LUT_STRIDE, buf[b][4], c * GORT_LUT_STRIDE * sizeof(double), cudaMemcpyDeviceToHost, B), "forward: lut");
-        TRYCUDA(ctx, cudaEventRecord(ctx->fwd_ev[4 + b], B), "cudaEventRecord");
+        // -- stream D: results of this chunk --
+        TRYCUDA(ctx, cudaStreamWaitEvent(D, ctx->fwd_ev[2 + b], 0), "cudaStreamWaitEvent");
+        TRYCUDA(ctx, cudaMemcpyAsync(rsurf + m0 * G * W, buf[b][8], c * G * W * sizeof(double), cudaMemcpyDeviceToHost, D), "forward: rsurf");
+        if (lut_out) TRYCUDA(ctx, cudaMemcpyAsync(lut_out + m0 * GORT_LUT_STRIDE, buf[b][4], c * GORT_LUT_STRIDE * sizeof(double), cudaMemcpyDeviceToHost, D), "forward: lut");
+        TRYCUDA(ctx, cudaEventRecord(ctx->fwd_ev[4 + b], D), "cudaEventRecord");
     }
+    TRYCUDA(ctx, cudaStreamSynchronize(D), "gort_forward_batch");
     TRYCUDA(ctx, cudaStreamSynchronize(B), "gort_forward_batch");
     TRYCUDA(ctx, cudaStreamSynchronize(A), "gort_forward_batch");
     note_other_work(ctx);

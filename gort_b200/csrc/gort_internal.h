@@ -11,7 +11,8 @@
 struct gort_ctx {
     int device;
     cudaStream_t stream;
-    cudaStream_t copy_stream;          // second stream of gort_forward_batch (copies under kernels)
+    cudaStream_t copy_stream;          // gort_forward_batch: inputs of the next chunk under the kernels of this one
+    cudaStream_t copy_stream_out;      // gort_forward_batch: results of the previous chunk under the kernels of this one
     cudaEvent_t fwd_ev[6];             // its per-buffer events: inputs ready, kernels done, outputs copied (x2)
     char err[512];
     long launches;
